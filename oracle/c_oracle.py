@@ -1,0 +1,135 @@
+"""ctypes loader for the plain-C oracle (``x360_oracle.c``).
+
+CPU ORACLE — TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libx360_oracle.so")
+_lib = None
+
+INTERP_LINEAR = 0
+INTERP_LANCZOS4 = 1
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle with the committed Makefile (gcc only)."""
+    src = os.path.join(_HERE, "x360_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libx360_oracle.so"])
+    return _SO
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        c_u8p = ctypes.POINTER(ctypes.c_uint8)
+        c_f32p = ctypes.POINTER(ctypes.c_float)
+        c_f64p = ctypes.POINTER(ctypes.c_double)
+        c_i64p = ctypes.POINTER(ctypes.c_int64)
+        c_i16p = ctypes.POINTER(ctypes.c_int16)
+        L.orc_focal.restype = ctypes.c_double
+        L.orc_focal.argtypes = [ctypes.c_int, ctypes.c_double]
+        L.orc_make_map.restype = None
+        L.orc_make_map.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, c_f64p, c_f32p, c_f32p]
+        for name in ("orc_remap_linear", "orc_remap_lanczos4"):
+            fn = getattr(L, name)
+            fn.restype = None
+            fn.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p,
+                           ctypes.c_int, ctypes.c_int, c_u8p]
+        L.orc_lanczos4_table.restype = None
+        L.orc_lanczos4_table.argtypes = [c_i16p]
+        L.orc_blur_sums.restype = None
+        L.orc_blur_sums.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p, c_i64p]
+        L.orc_score_from_sums.restype = ctypes.c_double
+        L.orc_score_from_sums.argtypes = [ctypes.c_int64] * 3
+        L.orc_extract.restype = None
+        L.orc_extract.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f64p,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                  c_u8p, c_i64p, c_i64p]
+        _lib = L
+    return _lib
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(ctypes.POINTER(ty))
+
+
+def focal(dest_w: int, fov_deg: float) -> float:
+    return lib().orc_focal(int(dest_w), float(fov_deg))
+
+
+def make_map(src_h, src_w, dest_h, dest_w, fov_deg, R):
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    mx = np.empty((dest_h, dest_w), np.float32)
+    my = np.empty((dest_h, dest_w), np.float32)
+    lib().orc_make_map(src_h, src_w, dest_h, dest_w, float(fov_deg), _p(R, ctypes.c_double),
+                       _p(mx, ctypes.c_float), _p(my, ctypes.c_float))
+    return mx, my
+
+
+def remap(src, map_x, map_y, interp=INTERP_LINEAR):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    assert src.ndim == 3 and src.shape[2] == 3
+    mx = np.ascontiguousarray(map_x, dtype=np.float32)
+    my = np.ascontiguousarray(map_y, dtype=np.float32)
+    dh, dw = mx.shape
+    dst = np.empty((dh, dw, 3), np.uint8)
+    fn = lib().orc_remap_lanczos4 if interp == INTERP_LANCZOS4 else lib().orc_remap_linear
+    fn(_p(src, ctypes.c_uint8), src.shape[0], src.shape[1], _p(mx, ctypes.c_float),
+       _p(my, ctypes.c_float), dh, dw, _p(dst, ctypes.c_uint8))
+    return dst
+
+
+def lanczos4_table():
+    tab = np.empty((32 * 32, 8, 8), np.int16)
+    lib().orc_lanczos4_table(_p(tab, ctypes.c_int16))
+    return tab
+
+
+def blur_sums(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    assert ch in (1, 3)
+    s = ctypes.c_int64(0)
+    s2 = ctypes.c_int64(0)
+    lib().orc_blur_sums(_p(img, ctypes.c_uint8), img.shape[0], img.shape[1], ch,
+                        ctypes.byref(s), ctypes.byref(s2))
+    return s.value, s2.value
+
+
+def score_from_sums(s, s2, n):
+    return lib().orc_score_from_sums(int(s), int(s2), int(n))
+
+
+def blur_score(img):
+    if img is None:
+        return 0.0
+    s, s2 = blur_sums(img)
+    return score_from_sums(s, s2, img.shape[0] * img.shape[1])
+
+
+def extract(frames, R, d, fov_deg, interp=INTERP_LINEAR, want_scores=True):
+    """frames uint8 [F][H][W][3], R fp64 [V][3][3] -> (views u8 [F][V][d][d][3], sums)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    F, H, W, _ = frames.shape
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
+    V = R.shape[0]
+    out = np.empty((F, V, d, d, 3), np.uint8)
+    s = np.zeros((F, V), np.int64)
+    s2 = np.zeros((F, V), np.int64)
+    lib().orc_extract(_p(frames, ctypes.c_uint8), F, H, W, _p(R, ctypes.c_double), V, d,
+                      float(fov_deg), int(interp), _p(out, ctypes.c_uint8),
+                      _p(s, ctypes.c_int64) if want_scores else None,
+                      _p(s2, ctypes.c_int64) if want_scores else None)
+    if not want_scores:
+        return out, None, None
+    return out, s, s2
