@@ -1,0 +1,26 @@
+"""x360 — B200-native (sm_100a) equirectangular -> rectilinear extraction.
+
+Drop-in for ONE hot path of nicolasdiolez/360Extractor: camera-layout rays, on-the-fly
+``map_x/map_y``, the ``cv2.remap`` gather (bilinear / Lanczos4, wrap-around) and the fused
+Laplacian-variance blur score.  All pixel work runs in hand-written CUDA behind a C-ABI
+(``include/x360.h``, ``lib/libx360.so``); importing this package never falls back to a CPU path.
+
+The directory name starts with a digit, so import it with
+``importlib.import_module("360extractor_b200")`` or through the ``x360`` alias at the repo root.
+"""
+from ._capi import INTERP_LANCZOS4, INTERP_LINEAR, X360Error, launch_count, version
+from .blur_filter import BlurFilter
+from .extractor import Extractor, PinnedBuffer, remap, scores_from_sums
+from .geometry import GeometryProcessor, focal_length, rotation_stack
+from .image_utils import ImageUtils
+from .pipeline import ExtractionSession, ViewResult
+from .sharding import gather_sums, shard_bounds, shard_sizes
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter",
+    "PinnedBuffer", "remap", "scores_from_sums", "rotation_stack", "focal_length",
+    "gather_sums", "shard_bounds", "shard_sizes",
+    "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",
+]

@@ -1,0 +1,433 @@
+// x360_capi.cu — host side of libx360: the C-ABI declared in include/x360.h.
+//
+// One translation unit: kernels (x360_*.cuh) + plan management + the pipelined host path.
+// Built by 360extractor_b200/build.py with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU fallback anywhere in this file: every compute entry needs a CUDA device.
+#include "../../include/x360.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "x360_common.cuh"
+#include "x360_extract.cuh"
+#include "x360_lanczos.cuh"
+#include "x360_linear.cuh"
+#include "x360_misc.cuh"
+#include "x360_tables.hpp"
+
+using namespace x360;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(X360_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// geometry.py:141 — f = (0.5*dest_w) / tan(0.5*radians(fov_deg)); radians(x) = x*(pi/180)
+double focal_of(int out_w, double fov_deg)
+{
+    const double rad = fov_deg * (3.14159265358979323846 / 180.0);
+    return (0.5 * (double)out_w) / std::tan(0.5 * rad);
+}
+
+Geom make_geom(int W, int H, int ow, int oh, double fov_deg)
+{
+    Geom g;
+    g.W = W; g.H = H; g.ow = ow; g.oh = oh;
+    g.tiles_x = (ow + kTile - 1) / kTile;
+    g.tiles_y = (oh + kTile - 1) / kTile;
+    g.f = focal_of(ow, fov_deg);
+    g.cx = ow / 2.0;
+    g.cy = oh / 2.0;
+    return g;
+}
+
+int check_dims(int W, int H, int ow, int oh)
+{
+    if (W < 2 || H < 2 || W > 32767 || H > 32767)
+        return fail(X360_E_INVALID, "source size %dx%d outside [2, 32767] (cv2.remap's int16 coordinate range)", W, H);
+    if (ow < 1 || oh < 1 || ow > 32768 || oh > 32768) return fail(X360_E_INVALID, "bad output size %dx%d", ow, oh);
+    if ((size_t)W * H * 3 > 0xffffff00ull) return fail(X360_E_INVALID, "frame larger than 4 GiB");
+    return X360_OK;
+}
+
+typedef void (*extract_fn)(const ExtractArgs);
+
+struct Variant {
+    extract_fn fn;
+    int min_blocks;
+};
+
+Variant pick_variant(int interp, bool scores)
+{
+    if (interp == X360_INTERP_LANCZOS4)
+        return scores ? Variant{extract_direct<LanczosSampler, true, 2>, 2} : Variant{extract_direct<LanczosSampler, false, 2>, 2};
+    return scores ? Variant{extract_direct<LinearSampler, true, 3>, 3} : Variant{extract_direct<LinearSampler, false, 4>, 4};
+}
+
+}  // namespace
+
+struct x360_plan {
+    x360_params p;
+    Geom g;
+    int sm_count = 0;
+    double *d_R = nullptr;
+    int16_t *d_lz = nullptr;
+    // pipelined host path
+    int chunk = 0;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
+    uint8_t *d_frames[2] = {}, *d_views[2] = {};
+    long long *d_sums[2] = {};
+    bool pipe_ready = false;
+};
+
+static int plan_grid(const x360_plan *pl, bool scores)
+{
+    const Variant v = pick_variant(pl->p.interp, scores);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    const int n_tiles = pl->p.n_views * pl->g.tiles_x * pl->g.tiles_y;
+    const int cap = pl->sm_count * occ;
+    return n_tiles < cap ? n_tiles : cap;
+}
+
+extern "C" {
+
+const char *x360_last_error(void) { return g_err.c_str(); }
+const char *x360_version(void) { return "x360 0.1.0 (sm_100a; abi 1)"; }
+int64_t x360_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int x360_lanczos4_table(int16_t *out)
+{
+    if (!out) return fail(X360_E_INVALID, "null table pointer");
+    const std::vector<int16_t> t = lanczos4_q15_table();
+    memcpy(out, t.data(), t.size() * sizeof(int16_t));
+    return X360_OK;
+}
+
+double x360_focal(int32_t out_w, double fov_deg) { return focal_of(out_w, fov_deg); }
+
+int x360_plan_create(const x360_params *params, x360_plan **out_plan)
+{
+    if (!params || !out_plan) return fail(X360_E_INVALID, "null argument");
+    if (params->struct_size != (int32_t)sizeof(x360_params))
+        return fail(X360_E_INVALID, "x360_params.struct_size %d != %zu (ABI mismatch)", params->struct_size, sizeof(x360_params));
+    *out_plan = nullptr;
+    if (int rc = check_dims(params->src_w, params->src_h, params->out_w, params->out_h)) return rc;
+    if (params->n_views < 1 || !params->R) return fail(X360_E_INVALID, "need at least one view and its rotation matrix");
+    if (!(params->fov_deg > 0.0 && params->fov_deg < 180.0)) return fail(X360_E_INVALID, "fov_deg %g outside (0, 180)", params->fov_deg);
+    if (params->interp != X360_INTERP_LINEAR && params->interp != X360_INTERP_LANCZOS4)
+        return fail(X360_E_INVALID, "unknown interp %d", params->interp);
+    if (params->path != X360_PATH_AUTO && params->path != X360_PATH_DIRECT)
+        return fail(X360_E_UNSUPPORTED, "path %d is not built into this library", params->path);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
+    if (params->device < 0 || params->device >= n_dev) return fail(X360_E_INVALID, "device %d out of range [0, %d)", params->device, n_dev);
+    CU(cudaSetDevice(params->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, params->device));
+    if (prop.major != 10)
+        return fail(X360_E_UNSUPPORTED, "device %d is sm_%d%d; libx360 is built for sm_100a only", params->device, prop.major, prop.minor);
+
+    x360_plan *pl = new (std::nothrow) x360_plan();
+    if (!pl) return fail(X360_E_NOMEM, "out of host memory");
+    pl->p = *params;
+    pl->p.R = nullptr;
+    pl->g = make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg);
+    pl->sm_count = prop.multiProcessorCount;
+    pl->chunk = params->max_batch > 0 ? params->max_batch : 8;
+    cudaError_t e = cudaMalloc(&pl->d_R, sizeof(double) * 9 * params->n_views);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_R, params->R, sizeof(double) * 9 * params->n_views, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && params->interp == X360_INTERP_LANCZOS4) {
+        const std::vector<int16_t> t = lanczos4_q15_table();
+        e = cudaMalloc(&pl->d_lz, t.size() * sizeof(int16_t));
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_lz, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        x360_plan_destroy(pl);
+        return fail(X360_E_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out_plan = pl;
+    return X360_OK;
+}
+
+int x360_plan_destroy(x360_plan *pl)
+{
+    if (!pl) return X360_OK;
+    cudaSetDevice(pl->p.device);
+    cudaFree(pl->d_R);
+    cudaFree(pl->d_lz);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(pl->d_frames[i]);
+        cudaFree(pl->d_views[i]);
+        cudaFree(pl->d_sums[i]);
+        if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
+        if (pl->ev_k[i]) cudaEventDestroy(pl->ev_k[i]);
+        if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
+    }
+    if (pl->s_in) cudaStreamDestroy(pl->s_in);
+    if (pl->s_k) cudaStreamDestroy(pl->s_k);
+    if (pl->s_out) cudaStreamDestroy(pl->s_out);
+    delete pl;
+    return X360_OK;
+}
+
+int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *block, int32_t *smem_bytes)
+{
+    if (!pl) return fail(X360_E_INVALID, "null plan");
+    if (path) *path = X360_PATH_DIRECT;
+    if (grid) *grid = plan_grid(pl, false);
+    if (block) *block = kThreads;
+    if (smem_bytes) *smem_bytes = (int32_t)sizeof(TileSmem);
+    return X360_OK;
+}
+
+int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, uint8_t *out_views,
+                        int64_t *sum_lap, int64_t *sum_lap2, void *cuda_stream)
+{
+    if (!pl || !frames || !out_views) return fail(X360_E_INVALID, "null argument");
+    if (n_frames < 0) return fail(X360_E_INVALID, "negative frame count");
+    if ((sum_lap == nullptr) != (sum_lap2 == nullptr)) return fail(X360_E_INVALID, "sum_lap and sum_lap2 must both be given or both be NULL");
+    if (n_frames == 0) return X360_OK;
+    CU(cudaSetDevice(pl->p.device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool scores = sum_lap != nullptr;
+    ExtractArgs a;
+    a.g = pl->g;
+    a.frames = frames;
+    a.out = out_views;
+    a.sum_lap = (long long *)sum_lap;
+    a.sum_lap2 = (long long *)sum_lap2;
+    a.R = pl->d_R;
+    a.lz_tab = pl->d_lz;
+    a.F = n_frames;
+    a.V = pl->p.n_views;
+    a.n_tiles = pl->p.n_views * pl->g.tiles_x * pl->g.tiles_y;
+    a.aligned = ((uintptr_t)frames % 4 == 0) && (pl->g.W % 4 == 0) && ((uintptr_t)out_views % 16 == 0) &&
+                (((size_t)pl->g.ow * 3) % 16 == 0);
+    if (scores) {
+        CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
+        CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
+    }
+    const Variant v = pick_variant(pl->p.interp, scores);
+    const int grid = plan_grid(pl, scores);
+    v.fn<<<grid, kThreads, 0, st>>>(a);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    return X360_OK;
+}
+
+static int pipe_setup(x360_plan *pl)
+{
+    if (pl->pipe_ready) return X360_OK;
+    const size_t fb = (size_t)pl->g.H * pl->g.W * 3, vb = (size_t)pl->g.oh * pl->g.ow * 3 * pl->p.n_views;
+    CU(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pl->s_k, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pl->ev_k[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
+        CU(cudaMalloc(&pl->d_frames[i], fb * pl->chunk));
+        CU(cudaMalloc(&pl->d_views[i], vb * pl->chunk));
+        CU(cudaMalloc(&pl->d_sums[i], sizeof(long long) * 2 * pl->chunk * pl->p.n_views));
+    }
+    pl->pipe_ready = true;
+    return X360_OK;
+}
+
+int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, uint8_t *out_views,
+                      int64_t *sum_lap, int64_t *sum_lap2)
+{
+    if (!pl || !frames || !out_views) return fail(X360_E_INVALID, "null argument");
+    if (n_frames < 0) return fail(X360_E_INVALID, "negative frame count");
+    if ((sum_lap == nullptr) != (sum_lap2 == nullptr)) return fail(X360_E_INVALID, "sum_lap and sum_lap2 must both be given or both be NULL");
+    if (n_frames == 0) return X360_OK;
+    CU(cudaSetDevice(pl->p.device));
+    if (int rc = pipe_setup(pl)) return rc;
+    const int V = pl->p.n_views;
+    const size_t fb = (size_t)pl->g.H * pl->g.W * 3, vb = (size_t)pl->g.oh * pl->g.ow * 3 * V;
+    const bool scores = sum_lap != nullptr;
+    int c = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += pl->chunk, ++c) {
+        const int b = c & 1;
+        const int n = (n_frames - f0 < pl->chunk) ? n_frames - f0 : pl->chunk;
+        // upload: the input buffer is free once the kernel of chunk c-2 has run
+        if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
+        CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+        CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
+        // compute: needs the upload, and the download of chunk c-2 out of this output buffer
+        CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));
+        long long *ds = scores ? pl->d_sums[b] : nullptr;
+        long long *ds2 = scores ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
+        if (int rc = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return rc;
+        CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
+        // download
+        CU(cudaStreamWaitEvent(pl->s_out, pl->ev_k[b], 0));
+        CU(cudaMemcpyAsync(out_views + (size_t)f0 * vb, pl->d_views[b], vb * n, cudaMemcpyDeviceToHost, pl->s_out));
+        if (scores) {
+            CU(cudaMemcpyAsync(sum_lap + (size_t)f0 * V, ds, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
+            CU(cudaMemcpyAsync(sum_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
+        }
+        CU(cudaEventRecord(pl->ev_out[b], pl->s_out));
+    }
+    CU(cudaStreamSynchronize(pl->s_out));
+    CU(cudaStreamSynchronize(pl->s_k));
+    CU(cudaStreamSynchronize(pl->s_in));
+    return X360_OK;
+}
+
+int x360_extract(x360_plan *pl, const uint8_t *frames, int32_t n_frames, uint8_t *out_views,
+                 int64_t *sum_lap, int64_t *sum_lap2, void *cuda_stream)
+{
+    if (!pl || !frames) return fail(X360_E_INVALID, "null argument");
+    CU(cudaSetDevice(pl->p.device));
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, frames);
+    if (e != cudaSuccess) { cudaGetLastError(); }
+    const bool on_device = (e == cudaSuccess) && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+    return on_device ? x360_extract_device(pl, frames, n_frames, out_views, sum_lap, sum_lap2, cuda_stream)
+                     : x360_extract_host(pl, frames, n_frames, out_views, sum_lap, sum_lap2);
+}
+
+int x360_make_maps(x360_plan *pl, int32_t view, float *map_x, float *map_y)
+{
+    if (!pl || !map_x || !map_y) return fail(X360_E_INVALID, "null argument");
+    if (view < 0 || view >= pl->p.n_views) return fail(X360_E_INVALID, "view %d out of range", view);
+    CU(cudaSetDevice(pl->p.device));
+    const size_t n = (size_t)pl->g.ow * pl->g.oh;
+    float *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(float) * 2 * n));
+    const dim3 grid((pl->g.ow + 31) / 32, (pl->g.oh + 7) / 8);
+    make_maps_kernel<<<grid, 256>>>(pl->g, pl->d_R + 9 * view, d, d + n);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(map_x, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(map_y, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(X360_E_CUDA, "make_maps failed: %s", cudaGetErrorString(e));
+    return X360_OK;
+}
+
+int x360_remap_maps(int32_t device, const uint8_t *src, int32_t src_h, int32_t src_w, const float *map_x,
+                    const float *map_y, int32_t out_h, int32_t out_w, int32_t interp, uint8_t *dst)
+{
+    if (!src || !map_x || !map_y || !dst) return fail(X360_E_INVALID, "null argument");
+    if (int rc = check_dims(src_w, src_h, out_w, out_h)) return rc;
+    if (interp != X360_INTERP_LINEAR && interp != X360_INTERP_LANCZOS4) return fail(X360_E_INVALID, "unknown interp %d", interp);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const Geom g = make_geom(src_w, src_h, out_w, out_h, 90.0);
+    const size_t sb = (size_t)src_h * src_w * 3, n = (size_t)out_h * out_w;
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    float *d_map = nullptr;
+    int16_t *d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&d_src, sb);
+    if (e == cudaSuccess) e = cudaMalloc(&d_dst, n * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&d_map, sizeof(float) * 2 * n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_src, src, sb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_map, map_x, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_map + n, map_y, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && interp == X360_INTERP_LANCZOS4) {
+        const std::vector<int16_t> t = lanczos4_q15_table();
+        e = cudaMalloc(&d_tab, t.size() * sizeof(int16_t));
+        if (e == cudaSuccess) e = cudaMemcpy(d_tab, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        const dim3 grid((out_w + 31) / 32, (out_h + 7) / 8);
+        if (interp == X360_INTERP_LANCZOS4)
+            remap_maps_kernel<LanczosSampler><<<grid, 256>>>(g, d_src, d_map, d_map + n, d_tab, d_dst);
+        else
+            remap_maps_kernel<LinearSampler><<<grid, 256>>>(g, d_src, d_map, d_map + n, d_tab, d_dst);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(dst, d_dst, n * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_map); cudaFree(d_tab);
+    if (e != cudaSuccess) return fail(X360_E_CUDA, "remap_maps failed: %s", cudaGetErrorString(e));
+    return X360_OK;
+}
+
+int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, int32_t channels,
+                   int64_t *sum_lap, int64_t *sum_lap2)
+{
+    if (!image || !sum_lap || !sum_lap2) return fail(X360_E_INVALID, "null argument");
+    if (h < 1 || w < 1 || (channels != 1 && channels != 3)) return fail(X360_E_INVALID, "bad image %dx%dx%d", h, w, channels);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t n = (size_t)h * w;
+    uint8_t *d_img = nullptr, *d_gray = nullptr;
+    long long *d_s = nullptr;
+    cudaError_t e = cudaMalloc(&d_img, n * channels);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, sizeof(long long) * 2);
+    if (e == cudaSuccess) e = cudaMemset(d_s, 0, sizeof(long long) * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(d_img, image, n * channels, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && channels == 3) {
+        e = cudaMalloc(&d_gray, n);
+        if (e == cudaSuccess) {
+            gray_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_img, d_gray, n);
+            g_launches.fetch_add(1);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) {
+        size_t blocks = (n + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        laplacian_sums_kernel<<<(unsigned)blocks, 256>>>(channels == 3 ? d_gray : d_img, h, w, d_s, d_s + 1);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    long long hs[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(hs, d_s, sizeof hs, cudaMemcpyDeviceToHost);
+    cudaFree(d_img); cudaFree(d_gray); cudaFree(d_s);
+    if (e != cudaSuccess) return fail(X360_E_CUDA, "blur_sums failed: %s", cudaGetErrorString(e));
+    *sum_lap = hs[0];
+    *sum_lap2 = hs[1];
+    return X360_OK;
+}
+
+int x360_host_alloc(size_t bytes, void **out_ptr)
+{
+    if (!out_ptr) return fail(X360_E_INVALID, "null argument");
+    CU(cudaHostAlloc(out_ptr, bytes, cudaHostAllocDefault));
+    return X360_OK;
+}
+
+int x360_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return X360_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""``Extractor``: one libx360 plan = one job's geometry, and the batched hot-path call.
+
+Replaces the reference's per-job map build (src/core/processor.py:245-265) and the body of its
+per-view loop (src/core/processor.py:327-342: ``cv2.remap`` + ``calculate_blur_score``) with one
+call per frame batch.  Every pixel is computed by the CUDA library; nothing here has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._capi import INTERP_LANCZOS4, INTERP_LINEAR, Params, check, lib, ptr
+
+
+def interp_code(interpolation_mode) -> int:
+    """'lanczos' -> INTER_LANCZOS4, anything else -> INTER_LINEAR (src/core/processor.py:199-200)."""
+    if isinstance(interpolation_mode, (int, np.integer)):
+        return int(interpolation_mode)
+    return INTERP_LANCZOS4 if interpolation_mode == "lanczos" else INTERP_LINEAR
+
+
+def scores_from_sums(sum_lap, sum_lap2, n_pixels: int) -> np.ndarray:
+    """Population variance of the Laplacian (ndarray.var, ddof=0; src/utils/image_utils.py:27) from
+    the exact integer sums the kernel returns: s2/N - (s/N)^2 in fp64."""
+    s = np.asarray(sum_lap, dtype=np.float64)
+    s2 = np.asarray(sum_lap2, dtype=np.float64)
+    mean = s / float(n_pixels)
+    return s2 / float(n_pixels) - mean * mean
+
+
+class Extractor:
+    """Plan wrapper.  ``R`` is fp64 ``[V][3][3]`` from ``GeometryProcessor.get_rotation_matrix``."""
+
+    def __init__(self, src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *,
+                 out_h=None, device=0, max_batch=8, path=_capi.PATH_AUTO):
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
+        self.src_h, self.src_w = int(src_h), int(src_w)
+        self.out_w = int(out_res)
+        self.out_h = int(out_h) if out_h is not None else int(out_res)
+        self.n_views = int(R.shape[0])
+        self.fov_deg = float(fov_deg)
+        self.interp = interp_code(interpolation_mode)
+        self.device = int(device)
+        self._R = R
+        p = Params()
+        p.struct_size = ctypes.sizeof(Params)
+        p.src_w, p.src_h = self.src_w, self.src_h
+        p.out_w, p.out_h = self.out_w, self.out_h
+        p.fov_deg = self.fov_deg
+        p.interp = self.interp
+        p.n_views = self.n_views
+        p.R = R.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        p.device = self.device
+        p.max_batch = int(max_batch)
+        p.path = int(path)
+        self._plan = ctypes.c_void_p()
+        check(lib().x360_plan_create(ctypes.byref(p), ctypes.byref(self._plan)))
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_plan", None):
+            lib().x360_plan_destroy(self._plan)
+            self._plan = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- shapes --------------------------------------------------------------------------------
+    @property
+    def frame_shape(self):
+        return (self.src_h, self.src_w, 3)
+
+    def views_shape(self, n_frames):
+        return (n_frames, self.n_views, self.out_h, self.out_w, 3)
+
+    @property
+    def pixels_per_view(self):
+        return self.out_h * self.out_w
+
+    def info(self):
+        vals = [ctypes.c_int32() for _ in range(4)]
+        check(lib().x360_plan_info(self._plan, *[ctypes.byref(v) for v in vals]))
+        return {"path": vals[0].value, "grid": vals[1].value, "block": vals[2].value, "smem_bytes": vals[3].value}
+
+    # -- the hot path --------------------------------------------------------------------------
+    def extract(self, frames, want_scores=False, out=None):
+        """frames uint8 ``[F][H][W][3]`` (numpy / pinned numpy) -> ``(views uint8 [F][V][d][d][3], scores)``.
+
+        ``scores`` is float64 ``[F][V]`` (or ``None``).  Host buffers: upload, kernels and download
+        are pipelined in the library on side streams."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        if frames.shape[1:] != self.frame_shape:
+            raise ValueError(f"frames shape {frames.shape} does not match plan {self.frame_shape}")
+        F = frames.shape[0]
+        if out is None:
+            out = np.empty(self.views_shape(F), np.uint8)
+        elif out.shape != self.views_shape(F) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 array of shape %r" % (self.views_shape(F),))
+        s = s2 = None
+        if want_scores:
+            s = np.zeros((F, self.n_views), np.int64)
+            s2 = np.zeros((F, self.n_views), np.int64)
+        check(lib().x360_extract_host(self._plan, ptr(frames), F, ptr(out), ptr(s), ptr(s2)))
+        scores = scores_from_sums(s, s2, self.pixels_per_view) if want_scores else None
+        return out, scores
+
+    def extract_sums(self, frames, out=None):
+        """Like ``extract`` but returns the raw int64 ``(sum L, sum L^2)`` arrays."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        F = frames.shape[0]
+        if out is None:
+            out = np.empty(self.views_shape(F), np.uint8)
+        s = np.zeros((F, self.n_views), np.int64)
+        s2 = np.zeros((F, self.n_views), np.int64)
+        check(lib().x360_extract_host(self._plan, ptr(frames), F, ptr(out), ptr(s), ptr(s2)))
+        return out, s, s2
+
+    def extract_device(self, frames, out, sum_lap=None, sum_lap2=None, stream=None):
+        """Device-resident batch (torch CUDA tensors or raw device addresses); asynchronous on ``stream``.
+
+        frames ``[F][H][W][3]`` uint8, out ``[F][V][d][d][3]`` uint8, sums int64 ``[F][V]`` or None."""
+        F = int(frames.shape[0])
+        st = None
+        if stream is not None:
+            st = getattr(stream, "cuda_stream", stream)
+        check(lib().x360_extract_device(self._plan, ptr(frames), F, ptr(out), ptr(sum_lap), ptr(sum_lap2), st))
+
+    # -- materialised maps (compatibility entry) -----------------------------------------------
+    def make_maps(self, view: int):
+        mx = np.empty((self.out_h, self.out_w), np.float32)
+        my = np.empty((self.out_h, self.out_w), np.float32)
+        check(lib().x360_make_maps(self._plan, int(view), ptr(mx), ptr(my)))
+        return mx, my
+
+
+def remap(frame, map_x, map_y, interpolation=INTERP_LINEAR, device=0):
+    """GPU ``cv2.remap(frame, map_x, map_y, interp, borderMode=cv2.BORDER_WRAP)`` for caller-held maps
+    (src/core/processor.py:334).  ``interpolation``: 'linear' / 'lanczos' or an ``INTERP_*`` code."""
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    if frame.ndim != 3 or frame.shape[2] != 3:
+        raise ValueError("frame must be uint8 [H][W][3] (BGR)")
+    mx = np.ascontiguousarray(map_x, dtype=np.float32)
+    my = np.ascontiguousarray(map_y, dtype=np.float32)
+    if mx.shape != my.shape or mx.ndim != 2:
+        raise ValueError("map_x / map_y must be 2-D float32 arrays of equal shape")
+    dst = np.empty(mx.shape + (3,), np.uint8)
+    check(lib().x360_remap_maps(int(device), ptr(frame), frame.shape[0], frame.shape[1], ptr(mx), ptr(my),
+                                mx.shape[0], mx.shape[1], interp_code(interpolation), ptr(dst)))
+    return dst
+
+
+class PinnedBuffer:
+    """A page-locked host array from ``x360_host_alloc`` (for the pipelined host path)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = ctypes.c_void_p()
+        check(lib().x360_host_alloc(max(nbytes, 1), ctypes.byref(self._ptr)))
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().x360_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

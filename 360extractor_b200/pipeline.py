@@ -1,0 +1,108 @@
+"""Per-job driver for the hot path: the caller contract of ``ProcessingWorker.process_video``.
+
+Covers exactly the slices of src/core/processor.py that sit on the path:
+  :165-171,199-200,219-221  settings read (resolution, fov, camera_count, pitch_offset, layout_mode,
+                            interpolation_mode, blur keys)
+  :245-265                  views + one "map" per active camera        -> one libx360 plan
+  :327-342                  per frame, per view: remap (+ blur score)  -> one batched GPU call
+  :341-376                  blur accept/reject, in (frame, view) order -> ``BlurFilter`` replay
+Decode, sharpening, AI masking, naming and saving stay with the caller (out of scope).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .blur_filter import BlurFilter
+from .extractor import Extractor
+from .geometry import GeometryProcessor, rotation_stack
+from .sharding import gather_sums, shard_bounds
+
+
+@dataclass
+class ViewResult:
+    frame_index: int          # index into the batch passed to ``process``
+    camera: str               # view name, used as the camera token of the output file name (processor.py:446)
+    image: np.ndarray         # uint8 [d][d][3] BGR, C-contiguous, owned by the caller
+    score: Optional[float]    # Laplacian variance, None when the blur filter is off
+
+
+class ExtractionSession:
+    """One job: settings dict + source size -> plan; ``process(frames)`` -> kept views."""
+
+    def __init__(self, settings: dict, src_h: int, src_w: int, device: int = 0, max_batch: int = 8):
+        self.settings = settings
+        self.out_res = settings.get("resolution", 2048)                 # job.py:40
+        self.fov = settings.get("fov", 90)                              # processor.py:166
+        camera_count = settings.get("camera_count", 6)                  # processor.py:167
+        pitch_offset = settings.get("pitch_offset", 0)                  # processor.py:168
+        layout_mode = settings.get("layout_mode", "ring")               # processor.py:169
+        if layout_mode == "adaptive":                                   # legacy alias, processor.py:170-171
+            layout_mode = "ring"
+        self.interpolation_mode = settings.get("interpolation_mode", "linear")
+        self.blur = BlurFilter.from_settings(settings)
+        self.views = GeometryProcessor.generate_views(camera_count, pitch_offset=pitch_offset, layout_mode=layout_mode)
+        self.active_cameras = settings.get("active_cameras", None)      # job.py:12
+        self.names, R = rotation_stack(self.views, self.active_cameras)
+        self.src_h, self.src_w = int(src_h), int(src_w)
+        self.extractor = None
+        if len(self.names):
+            self.extractor = Extractor(src_h, src_w, self.out_res, self.fov, R, self.interpolation_mode,
+                                       device=device, max_batch=max_batch)
+
+    def close(self):
+        if self.extractor is not None:
+            self.extractor.close()
+            self.extractor = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def extract_batch(self, frames):
+        """Raw batch call: ``(views uint8 [F][V][d][d][3], scores float64 [F][V] or None)``."""
+        if self.extractor is None:
+            F = len(frames)
+            return np.empty((F, 0, self.out_res, self.out_res, 3), np.uint8), (np.empty((F, 0)) if self.blur.enabled else None)
+        return self.extractor.extract(frames, want_scores=self.blur.enabled)
+
+    def process(self, frames) -> List[ViewResult]:
+        """Batch equivalent of the per-frame view loop: returns the kept views in (frame, view) order."""
+        views, scores = self.extract_batch(frames)
+        kept: List[ViewResult] = []
+        for f in range(views.shape[0]):
+            for v, name in enumerate(self.names):
+                score = float(scores[f, v]) if scores is not None else None
+                if self.blur.accept(score):
+                    kept.append(ViewResult(f, name, views[f, v], score))
+        return kept
+
+    def process_sharded(self, frames, rank: int, world_size: int, group=None):
+        """Frame-sharded variant: this rank reprojects frames ``shard_bounds(F, world, rank)``, the
+        score sums are all-gathered and every rank replays the blur machine over the full table.
+
+        Returns ``(lo, local_views, keep)`` with ``keep`` a bool ``[F][V]`` table valid on every rank."""
+        F = len(frames)
+        lo, hi = shard_bounds(F, world_size, rank)
+        local = np.ascontiguousarray(frames[lo:hi])
+        V = len(self.names)
+        if self.extractor is None or not self.blur.enabled:
+            views = self.extract_batch(local)[0] if hi > lo else np.empty((0, V, self.out_res, self.out_res, 3), np.uint8)
+            return lo, views, np.ones((F, V), bool)
+        if hi > lo:
+            views, s, s2 = self.extractor.extract_sums(local)
+        else:
+            views = np.empty((0, V, self.out_res, self.out_res, 3), np.uint8)
+            s = s2 = np.zeros((0, V), np.int64)
+        gs, gs2 = gather_sums(s, s2, F, group=group)
+        from .extractor import scores_from_sums
+        scores = scores_from_sums(gs, gs2, self.extractor.pixels_per_view)
+        keep = np.array(self.blur.replay(scores), dtype=bool).reshape(F, V)
+        return lo, views, keep
+
+
+__all__ = ["ExtractionSession", "ViewResult"]

@@ -1,0 +1,149 @@
+/*
+ * x360.h — C-ABI of libx360 (B200 / sm_100a equirect -> rectilinear extraction).
+ *
+ * The reference (nicolasdiolez/360Extractor) has no FFI of its own: its boundary
+ * for this path is four Python call signatures plus the loop that calls them.
+ * Each entry point below names the reference interface it replaces (file:line
+ * relative to the reference root).  Plain C types only; no C++ types, no
+ * exceptions and no callbacks cross this ABI.  All functions return 0 on
+ * success or a negative X360_E_* code; the message is in x360_last_error()
+ * (thread-local).  There is no CPU fallback: every compute entry fails with
+ * X360_E_CUDA when no usable device is present.
+ *
+ * Threading: a plan is used from one thread at a time (the reference calls this
+ * path from exactly one worker thread, src/core/processor.py:52-78).
+ * Ownership: the caller owns every input/output buffer and keeps it alive until
+ * the stream is synchronised; a plan owns only device scratch, its constant
+ * tables and its streams/events.
+ */
+#ifndef X360_H_
+#define X360_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X360_ABI_VERSION 1
+
+/* error codes */
+#define X360_OK          0
+#define X360_E_INVALID  -1   /* bad argument */
+#define X360_E_CUDA     -2   /* CUDA runtime error / no device */
+#define X360_E_NOMEM    -3
+#define X360_E_UNSUPPORTED -4
+
+/* src/core/processor.py:199-200 — 'lanczos' => INTER_LANCZOS4, else INTER_LINEAR */
+#define X360_INTERP_LINEAR   0
+#define X360_INTERP_LANCZOS4 1
+
+/* kernel-path selector (x360_params.path): 0 lets the plan choose */
+#define X360_PATH_AUTO    0
+#define X360_PATH_DIRECT  1   /* taps gathered straight from global/L2 through L1 */
+#define X360_PATH_STAGED  2   /* per-tile source footprint staged in shared memory by bulk async copies */
+
+typedef struct x360_plan x360_plan;
+
+/*
+ * One plan = one job's geometry: replaces the per-job map build
+ *   src/core/processor.py:245-265  (generate_views -> create_rectilinear_map per active view)
+ * The maps themselves are never materialised: the plan keeps the per-view fp64
+ * rotation matrices and the kernels evaluate src/core/geometry.py:141-190 on the
+ * fly per output tile.
+ */
+typedef struct x360_params {
+    int32_t struct_size;      /* = sizeof(x360_params) */
+    int32_t src_w, src_h;     /* equirect frame, uint8 BGR [src_h][src_w][3]   (processor.py:250-254) */
+    int32_t out_w, out_h;     /* view size; the reference always passes out_res twice (processor.py:263-265) */
+    double  fov_deg;          /* horizontal FOV (geometry.py:141) */
+    int32_t interp;           /* X360_INTERP_* */
+    int32_t n_views;          /* emitted views (after the active_cameras filter, processor.py:259-261) */
+    const double *R;          /* [n_views][9] row-major fp64 from get_rotation_matrix (geometry.py:80-119),
+                                 built by the caller with the reference's own numpy ops */
+    int32_t device;           /* CUDA ordinal */
+    int32_t max_batch;        /* frames per pipelined chunk in x360_extract_host (0 = default 8) */
+    int32_t path;             /* X360_PATH_* */
+    int32_t reserved;
+} x360_params;
+
+int x360_plan_create(const x360_params *params, x360_plan **out_plan);
+int x360_plan_destroy(x360_plan *plan);
+
+/*
+ * The batched hot path: replaces the body of the per-view loop
+ *   src/core/processor.py:327-342   rect = cv2.remap(frame, map_x, map_y, interp, BORDER_WRAP)
+ *                                   score = ImageUtils.calculate_blur_score(rect)
+ * for n_frames frames x n_views views in one call.
+ *   frames     uint8 [n_frames][src_h][src_w][3]
+ *   out_views  uint8 [n_frames][n_views][out_h][out_w][3]
+ *   sum_lap / sum_lap2  int64 [n_frames][n_views], both NULL to skip the score
+ *       (exact integer sum of L and L^2 of the 4-neighbour Laplacian of the
+ *        Q15 gray view, src/utils/image_utils.py:22-27; score = s2/N - (s/N)^2, N = out_w*out_h)
+ *
+ * x360_extract_device: all pointers are DEVICE pointers on the plan's device;
+ *   work is enqueued on cuda_stream (a cudaStream_t, may be NULL) and the call
+ *   returns without synchronising.
+ * x360_extract_host: all pointers are HOST pointers (pinned for full speed);
+ *   frames are uploaded, processed and downloaded in chunks of max_batch frames
+ *   on the plan's own side streams (H2D / compute / D2H overlap); synchronous.
+ * x360_extract: dispatches on the kind of `frames` pointer (device vs host);
+ *   out/sum pointers must be of the same kind.
+ */
+int x360_extract_device(x360_plan *plan, const uint8_t *frames, int32_t n_frames,
+                        uint8_t *out_views, int64_t *sum_lap, int64_t *sum_lap2, void *cuda_stream);
+int x360_extract_host(x360_plan *plan, const uint8_t *frames, int32_t n_frames,
+                      uint8_t *out_views, int64_t *sum_lap, int64_t *sum_lap2);
+int x360_extract(x360_plan *plan, const uint8_t *frames, int32_t n_frames,
+                 uint8_t *out_views, int64_t *sum_lap, int64_t *sum_lap2, void *cuda_stream);
+
+/*
+ * Materialise one view's float32 maps (HOST pointers, [out_h][out_w] each):
+ * replaces GeometryProcessor.create_rectilinear_map (src/core/geometry.py:122-192)
+ * for callers that still want the arrays (tests/test_core.py:67-78, the GUI preview).
+ */
+int x360_make_maps(x360_plan *plan, int32_t view, float *map_x, float *map_y);
+
+/*
+ * Explicit-map remap, HOST pointers: replaces
+ *   cv2.remap(frame, map_x, map_y, interp, borderMode=cv2.BORDER_WRAP)   (processor.py:334, analyzer.py:63)
+ * for a caller that holds its own float32 maps.  src uint8 [src_h][src_w][3],
+ * maps float32 [out_h][out_w], dst uint8 [out_h][out_w][3].
+ */
+int x360_remap_maps(int32_t device, const uint8_t *src, int32_t src_h, int32_t src_w,
+                    const float *map_x, const float *map_y, int32_t out_h, int32_t out_w,
+                    int32_t interp, uint8_t *dst);
+
+/*
+ * Laplacian-variance sums of one HOST image (channels = 3 BGR or 1 gray):
+ * replaces ImageUtils.calculate_blur_score (src/utils/image_utils.py:6-27).
+ */
+int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, int32_t channels,
+                   int64_t *sum_lap, int64_t *sum_lap2);
+
+/*
+ * Host-only helpers (no device needed), exposed so the constant tables and the focal
+ * length the plan derives can be checked against the oracle without a GPU:
+ *   x360_lanczos4_table  int16 [32*32][8][8], entry fy*32+fx — cv2.remap's INTER_LANCZOS4 weights
+ *   x360_focal           f of src/core/geometry.py:141
+ */
+int x360_lanczos4_table(int16_t *out_tab);
+double x360_focal(int32_t out_w, double fov_deg);
+
+/* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
+int x360_host_alloc(size_t bytes, void **out_ptr);
+int x360_host_free(void *ptr);
+
+/* diagnostics */
+const char *x360_last_error(void);
+const char *x360_version(void);
+/* number of kernels this library has launched in this process (all plans) */
+int64_t x360_launch_count(void);
+/* which path the plan's extract kernel uses (X360_PATH_*), and its launch geometry */
+int x360_plan_info(const x360_plan *plan, int32_t *path, int32_t *grid, int32_t *block, int32_t *smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X360_H_ */

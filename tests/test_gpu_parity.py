@@ -1,0 +1,249 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the oracle and the
+golden fixtures.  Bit-exact for both interpolations (north_star allows 1 LSB for Lanczos4; the
+tolerance used here is 0), blur scores from exact integer sums (checked to 1e-12 relative against
+the reference's fp64 values; north_star's bound is 1e-4)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_json, noise_frame, smooth_frame, unhex
+
+pytestmark = pytest.mark.gpu
+
+LANCZOS_TOL_LSB = 0
+SCORE_RTOL = 1e-12
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def assert_same(got, want, what, tol=0):
+    if tol == 0:
+        if not np.array_equal(got, want):
+            bad = np.argwhere(got != want)
+            raise AssertionError(f"{what}: {len(bad)} differing bytes, first at {bad[0].tolist()}: "
+                                 f"got {got[tuple(bad[0])]} want {want[tuple(bad[0])]}")
+    else:
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max()
+        assert d <= tol, f"{what}: max |diff| {d} > {tol}"
+
+
+def rotations(x360, views, active=None):
+    return x360.rotation_stack(views, active)[1]
+
+
+# ---- golden fixtures (outputs of the real reference) -----------------------------------------
+def test_small_golden_cases(x360):
+    z = np.load(GOLDEN + "/small_cases.npz")
+    meta = load_json("small_cases.json")
+    src = z["src"]
+    for k, m in enumerate(meta):
+        R = np.array([unhex(v) for v in m["R"]]).reshape(1, 3, 3)
+        for mode, key in (("linear", "lin"), ("lanczos", "lan")):
+            with x360.Extractor(src.shape[0], src.shape[1], m["d"], m["fov"], R, mode) as ex:
+                out, scores = ex.extract(src[None], want_scores=True)
+                assert_same(out[0, 0], z[f"{key}{k}"], f"case {k} {mode}")
+                assert scores[0, 0] == pytest.approx(unhex(m[f"{key}_score"]), rel=SCORE_RTOL)
+                mx, my = ex.make_maps(0)
+                assert np.array_equal(mx, z[f"mx{k}"]) and np.array_equal(my, z[f"my{k}"]), f"maps case {k}"
+
+
+@pytest.mark.parametrize("case", ["cube,6,0,90", "ring,8,-20,90", "fibonacci,20,-20,110"])
+def test_known_answer_hashes(x360, case):
+    """512x1024 noise, d=256, sha256 over the views in generate_views order."""
+    k = load_json("kat_512x1024.json")
+    g = k["cases"][case]
+    layout, n, pitch, fov = case.split(",")
+    src = np.random.default_rng(12345).integers(0, 256, (512, 1024, 3), dtype=np.uint8)
+    views = x360.GeometryProcessor.generate_views(int(n), pitch_offset=int(pitch), layout_mode=layout)
+    R = rotations(x360, views)
+    assert [[float(v).hex() for v in r.reshape(-1)] for r in R] == g["R"]
+    for mode, key in (("linear", "linear"), ("lanczos", "lanczos")):
+        with x360.Extractor(512, 1024, 256, int(fov), R, mode) as ex:
+            out, scores = ex.extract(src[None], want_scores=True)
+        assert [sha(out[0, v]) for v in range(len(views))] == g[f"{key}_view_sha"]
+        assert sha(*[out[0, v] for v in range(len(views))]) == g[f"{key}_sha"]
+        want = np.array([unhex(s) for s in g[f"{key}_scores"]])
+        np.testing.assert_allclose(scores[0], want, rtol=SCORE_RTOL)
+
+
+# ---- seeded sweeps against the oracle ----------------------------------------------------------
+SWEEP = [
+    # (H, W, d, fov, layout, n, pitch, F)
+    (256, 512, 96, 90, "cube", 6, 0, 3),          # poles, seam, multi-frame double buffering
+    (256, 512, 96, 90, "cube", 6, -45, 2),
+    (192, 384, 80, 60, "ring", 8, -20, 2),
+    (192, 384, 64, 120, "ring", 3, 45, 1),
+    (200, 400, 95, 110, "fibonacci", 7, -20, 2),  # odd d: partial tiles, unaligned rows
+    (161, 322, 50, 90, "fibonacci", 5, 20, 2),    # W % 4 != 0: generic gather everywhere
+    (128, 256, 33, 100, "ring", 2, -90, 1),       # looking straight down
+    (96, 192, 130, 75, "ring", 4, 0, 1),          # magnification (d larger than the source arc)
+]
+
+
+@pytest.mark.parametrize("mode,interp", [("linear", 0), ("lanczos", 1)])
+@pytest.mark.parametrize("cfg", SWEEP)
+def test_sweep_against_oracle(x360, oracle, cfg, mode, interp):
+    H, W, d, fov, layout, n, pitch, F = cfg
+    frames = np.stack([noise_frame(100 + i, H, W) for i in range(F)])
+    views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout)
+    R = rotations(x360, views)
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, interp)
+    with x360.Extractor(H, W, d, fov, R, mode) as ex:
+        got, s, s2 = ex.extract_sums(frames)
+        got_ns, none = ex.extract(frames, want_scores=False)      # the no-score kernel variant
+    assert none is None
+    assert_same(got, want, f"{cfg} {mode}", LANCZOS_TOL_LSB if interp else 0)
+    assert_same(got_ns, want, f"{cfg} {mode} (no scores)", LANCZOS_TOL_LSB if interp else 0)
+    assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
+
+
+def test_roll_and_active_camera_subset(x360, oracle):
+    views = x360.GeometryProcessor.generate_views(12, 0, "ring")
+    names, R = x360.rotation_stack(views, active_cameras=[0, 3, 6, 9])
+    frame = noise_frame(8, 256, 512)
+    for mode, interp in (("linear", 0), ("lanczos", 1)):
+        want, _, _ = oracle.extract(frame[None], R, 64, 90, interp, want_scores=False)
+        with x360.Extractor(256, 512, 64, 90, R, mode) as ex:
+            got, _ = ex.extract(frame[None])
+        assert_same(got, want, f"active cameras {mode}")
+    R30 = x360.GeometryProcessor.get_rotation_matrix(33.0, -20.0, 30.0)[None]   # roll honoured (geometry.py:112-116)
+    want, _, _ = oracle.extract(frame[None], R30, 72, 100, 0, want_scores=False)
+    with x360.Extractor(256, 512, 72, 100, R30, "linear") as ex:
+        assert_same(ex.extract(frame[None])[0], want, "roll 30")
+
+
+def test_chunked_host_pipeline_matches_single_shot(x360, oracle):
+    """x360_extract_host splits the batch into max_batch chunks on side streams; ragged last chunk."""
+    H, W, d = 128, 256, 64
+    frames = np.stack([np.roll(noise_frame(i % 4, H, W), 37 * i, axis=1) for i in range(7)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(6, 0, "cube"))
+    want, ws, ws2 = oracle.extract(frames, R, d, 90, 0)
+    with x360.Extractor(H, W, d, 90, R, "linear", max_batch=3) as ex:
+        pinned = x360.PinnedBuffer(frames.shape)
+        pinned.array[...] = frames
+        got, s, s2 = ex.extract_sums(pinned.array)
+        got2, s_b, s2_b = ex.extract_sums(pinned.array)           # plan reuse
+    assert_same(got, want, "chunked pipeline")
+    assert np.array_equal(s, ws) and np.array_equal(s2, ws2)
+    assert np.array_equal(got, got2) and np.array_equal(s, s_b) and np.array_equal(s2, s2_b)
+    with x360.Extractor(H, W, d, 90, R, "linear") as ex:
+        out, sc = ex.extract(frames[:0], want_scores=True)         # empty batch
+        assert out.shape == (0, 6, d, d, 3) and sc.shape == (0, 6)
+
+
+def test_device_resident_path(x360, oracle):
+    """torch tensors on the device, kernel enqueued on the caller's stream (what bench.py times)."""
+    import torch
+    H, W, d = 192, 384, 96
+    frames = np.stack([smooth_frame(i, H, W) for i in range(4)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(8, -20, "ring"))
+    want, ws, ws2 = oracle.extract(frames, R, d, 90, 0)
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(frames).to(dev)
+    with x360.Extractor(H, W, d, 90, R, "linear") as ex:
+        d_out = torch.empty(ex.views_shape(4), dtype=torch.uint8, device=dev)
+        d_s = torch.full((4, 8), -1, dtype=torch.int64, device=dev)
+        d_s2 = torch.full((4, 8), -1, dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            before = x360.launch_count()
+            ex.extract_device(d_frames, d_out, d_s, d_s2, stream=side)
+            assert x360.launch_count() == before + 1
+        side.synchronize()
+        assert_same(d_out.cpu().numpy(), want, "device path")
+        assert np.array_equal(d_s.cpu().numpy(), ws) and np.array_equal(d_s2.cpu().numpy(), ws2)
+        ex.extract_device(d_frames, d_out, None, None, stream=torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert_same(d_out.cpu().numpy(), want, "device path, no scores")
+
+
+def test_explicit_map_remap_and_blur_score(x360, oracle):
+    b = load_json("blur.json")
+    edge = np.zeros((100, 100), np.uint8)
+    edge[:, 50:] = 255
+    assert x360.ImageUtils.calculate_blur_score(edge) == unhex(b["edge_100"]) == 1300.5      # test_core.py:84-93
+    assert x360.ImageUtils.calculate_blur_score(np.ones((100, 100), np.uint8) * 128) == 0.0  # test_core.py:95-103
+    assert x360.ImageUtils.calculate_blur_score(None) == 0.0                                 # test_core.py:105-108
+    rng = np.random.default_rng(99)
+    for name in ("color_100", "color_37x53", "gray_64x17", "color_2x2", "color_1x5", "color_5x1"):
+        img = rng.integers(0, 256, b[name]["shape"], dtype=np.uint8)
+        score = x360.ImageUtils.calculate_blur_score(img)
+        assert isinstance(score, float) and score >= 0                                        # test_core.py:110-117
+        assert score == pytest.approx(unhex(b[name]["score"]), rel=SCORE_RTOL, abs=1e-9)
+    # cv2.remap drop-in with caller-held maps (processor.py:334)
+    src = noise_frame(21, 120, 240)
+    R = x360.GeometryProcessor.get_rotation_matrix(200.0, -35.0, 0.0)
+    mx, my = x360.GeometryProcessor.create_rectilinear_map(120, 240, 70, 70, 95, 200.0, -35.0, 0.0)
+    omx, omy = oracle.make_map(120, 240, 70, 70, 95, R)
+    assert mx.shape == (70, 70) and mx.dtype == np.float32                                   # test_core.py:67-78
+    assert np.array_equal(mx, omx) and np.array_equal(my, omy)
+    for mode, interp in (("linear", 0), ("lanczos", 1)):
+        assert_same(x360.remap(src, mx, my, mode), oracle.remap(src, omx, omy, interp), f"remap {mode}")
+    # arbitrary (non-geometric) maps incl. out-of-range coordinates: BORDER_WRAP on both axes
+    rng = np.random.default_rng(4)
+    amx = rng.uniform(-300, 600, (40, 56)).astype(np.float32)
+    amy = rng.uniform(-200, 400, (40, 56)).astype(np.float32)
+    for mode, interp in (("linear", 0), ("lanczos", 1)):
+        assert_same(x360.remap(src, amx, amy, mode), oracle.remap(src, amx, amy, interp), f"wild maps {mode}")
+
+
+def test_session_mirrors_processor_loop(x360, oracle):
+    """ExtractionSession = processor.py:245-265 + :327-376 for a frame batch."""
+    settings = {"resolution": 64, "fov": 90, "camera_count": 6, "pitch_offset": -20, "layout_mode": "adaptive",
+                "interpolation_mode": "linear", "blur_filter_enabled": True, "smart_blur_enabled": True,
+                "blur_threshold": 500.0, "active_cameras": [0, 2, 4]}
+    frames = np.stack([smooth_frame(1, 128, 256), noise_frame(2, 128, 256), smooth_frame(3, 128, 256)])
+    with x360.ExtractionSession(settings, 128, 256) as sess:
+        assert sess.names == ["View_0", "View_2", "View_4"]          # 'adaptive' => ring (processor.py:170-171)
+        kept = sess.process(frames)
+    views = x360.GeometryProcessor.generate_views(6, -20, "ring")
+    _, R = x360.rotation_stack(views, [0, 2, 4])
+    want, s, s2 = oracle.extract(frames, R, 64, 90, 0)
+    scores = [[oracle.score_from_sums(s[f, v], s2[f, v], 64 * 64) for v in range(3)] for f in range(3)]
+    ref_keep = x360.BlurFilter(True, True, 500.0).replay(scores)
+    expect = [(f, ["View_0", "View_2", "View_4"][v]) for f in range(3) for v in range(3) if ref_keep[f][v]]
+    assert [(k.frame_index, k.camera) for k in kept] == expect
+    assert 0 < len(kept) < 9                                         # smooth frames rejected, noise kept
+    for k in kept:
+        v = ["View_0", "View_2", "View_4"].index(k.camera)
+        assert_same(k.image, want[k.frame_index, v], "kept view")
+        assert k.image.flags.c_contiguous and k.image.flags.writeable
+
+
+# ---- BASELINE.json configurations at full size ------------------------------------------------
+FULL = [
+    # name, (H, W), layout, n, pitch, active, d, fov, mode, F, views to check against the oracle
+    ("cfg1", (1920, 3840), "cube", 6, 0, None, 1024, 90, "linear", 1, [0, 2, 4, 5]),
+    ("cfg2", (2880, 5760), "ring", 8, 0, None, 1600, 90, "linear", 2, [0, 4]),
+    ("cfg3", (3840, 7680), "fibonacci", 20, -20, None, 1920, 90, "lanczos", 1, [0, 11]),
+    ("cfg4", (3840, 7680), "cube", 6, 0, None, 1920, 90, "linear", 2, [2, 4]),
+    ("cfg5", (5760, 11520), "ring", 12, 0, [0, 3, 6, 9], 2048, 90, "lanczos", 1, [2]),
+]
+
+
+@pytest.mark.parametrize("cfg", FULL, ids=[c[0] for c in FULL])
+def test_full_size_configs(x360, oracle, cfg):
+    name, (H, W), layout, n, pitch, active, d, fov, mode, F, check = cfg
+    interp = 1 if mode == "lanczos" else 0
+    base = noise_frame(0, H, W)
+    frames = np.stack([np.roll(base, 37 * i, axis=1) for i in range(F)])       # SURVEY.md 8(d) clip recipe
+    views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout)
+    names, R = x360.rotation_stack(views, active)
+    with x360.Extractor(H, W, d, fov, R, mode, max_batch=1) as ex:
+        got, s, s2 = ex.extract_sums(frames)
+        again, s_b, s2_b = ex.extract_sums(frames)
+    # size-independent properties: deterministic, every view differs, sums consistent with the pixels
+    assert np.array_equal(got, again) and np.array_equal(s, s_b) and np.array_equal(s2, s2_b)
+    assert len({sha(got[0, v]) for v in range(len(names))}) == len(names)
+    f = F - 1
+    for v in check:
+        want, ws, ws2 = oracle.extract(frames[f:f + 1], R[v:v + 1], d, fov, interp)
+        assert_same(got[f, v], want[0, 0], f"{name} frame {f} view {names[v]}", LANCZOS_TOL_LSB if interp else 0)
+        assert s[f, v] == ws[0, 0] and s2[f, v] == ws2[0, 0]
+        assert oracle.blur_sums(got[f, v]) == (s[f, v], s2[f, v])

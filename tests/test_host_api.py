@@ -1,0 +1,198 @@
+"""Host layer (no GPU): layouts, rotations, the C-ABI surface, the blur state machine.
+
+The TestGeometryProcessor block reads like the reference's tests/test_core.py:18-65 on purpose:
+same calls, same expectations, against the drop-in class."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_json, unhex
+
+
+# ---- reference tests/test_core.py:18-65, transposed onto the drop-in -------------------------
+def test_generate_views_ring_6(x360):
+    views = x360.GeometryProcessor.generate_views(6, pitch_offset=0, layout_mode="ring")
+    assert len(views) == 6
+    for (_, yaw, _, _), expected in zip(views, [0.0, 60.0, 120.0, 180.0, 240.0, 300.0]):
+        assert yaw == pytest.approx(expected, abs=0.05)
+
+
+def test_generate_views_cube(x360):
+    views = x360.GeometryProcessor.generate_views(12, layout_mode="cube")
+    assert len(views) == 6
+    names = [v[0] for v in views]
+    for n in ("Front", "Back", "Up", "Down"):
+        assert n in names
+
+
+def test_generate_views_fibonacci(x360):
+    for n in (4, 8, 16):
+        assert len(x360.GeometryProcessor.generate_views(n, layout_mode="fibonacci")) == n
+
+
+def test_generate_views_with_pitch_offset(x360):
+    for _, _, pitch, _ in x360.GeometryProcessor.generate_views(4, pitch_offset=-20, layout_mode="ring"):
+        assert pitch == -20
+
+
+def test_rotation_matrix_identity(x360):
+    R = x360.GeometryProcessor.get_rotation_matrix(0, 0, 0)
+    assert R.shape == (3, 3)
+    np.testing.assert_array_almost_equal(R, np.eye(3), decimal=5)
+
+
+# ---- bit-level pins from the real reference ---------------------------------------------------
+def test_layouts_bit_identical_to_reference(x360):
+    g = load_json("geometry.json")
+    for key, exp in g["views"].items():
+        layout, n, pitch = key.split(",")
+        got = x360.GeometryProcessor.generate_views(int(n), pitch_offset=int(pitch), layout_mode=layout)
+        want = [(a, unhex(b), unhex(c), d) for a, b, c, d in exp]
+        assert got == want, key
+
+
+def test_rotations_bit_identical_to_reference(x360):
+    g = load_json("geometry.json")
+    for key, exp in g["rotations"].items():
+        ypr = [unhex(s) for s in key.split(",")]
+        R = x360.GeometryProcessor.get_rotation_matrix(*ypr)
+        assert R.dtype == np.float64
+        assert [float(v).hex() for v in R.reshape(-1)] == exp, key
+    # the residues that decide the seam
+    R = x360.GeometryProcessor.get_rotation_matrix(180, 0, 0)
+    assert R[0, 2] == 1.2246467991473532e-16 and R[2, 0] == -1.2246467991473532e-16
+
+
+def test_rotation_stack_active_cameras(x360):
+    views = x360.GeometryProcessor.generate_views(12, 0, "ring")
+    names, R = x360.rotation_stack(views, active_cameras=[0, 3, 6, 9])
+    assert names == ["View_0", "View_3", "View_6", "View_9"] and R.shape == (4, 3, 3)
+    assert np.array_equal(R[1], x360.GeometryProcessor.get_rotation_matrix(90.0, 0, 0))
+    names, R = x360.rotation_stack(views, active_cameras=[])
+    assert names == [] and R.shape == (0, 3, 3)
+
+
+# ---- C-ABI surface ----------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(x360):
+    """Every function include/x360.h declares is exported by libx360.so and bound by _capi."""
+    hdr = open(os.path.join(ROOT, "include", "x360.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(x360_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 16
+    lib = ctypes.CDLL(x360._capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in x360.h but not exported"
+    assert declared == set(x360._capi.SYMBOLS), "ctypes binding and header disagree"
+    assert x360.version().startswith("x360 ")
+    assert x360.launch_count() >= 0
+
+
+def test_params_struct_layout_matches_header(x360):
+    P = x360._capi.Params
+    assert ctypes.sizeof(P) == 64            # 5*i32 (+4 pad) + f64 + 2*i32 + ptr + 4*i32
+    assert P.fov_deg.offset == 24 and P.R.offset == 40 and P.device.offset == 48
+
+
+def test_host_side_tables_match_oracle(x360, oracle):
+    tab = np.empty((1024, 8, 8), np.int16)
+    assert x360._capi.lib().x360_lanczos4_table(tab.ctypes.data) == 0
+    assert np.array_equal(tab, oracle.lanczos4_table())
+    assert (tab.reshape(1024, -1).astype(np.int64).sum(1) == 32768).all()
+    assert tab.min() == -5727 and tab.max() == 32767
+    for w, fov in [(1024, 90), (1600, 90), (1920, 110), (2048, 60), (1023, 120), (512, 73.5)]:
+        ref = (0.5 * w) / np.tan(0.5 * np.radians(fov))          # geometry.py:141
+        assert x360.focal_length(w, fov) == ref == oracle.focal(w, fov)
+
+
+def test_argument_errors_do_not_need_a_gpu(x360):
+    lib = x360._capi.lib()
+    assert lib.x360_plan_create(None, None) == -1
+    assert b"null" in lib.x360_last_error()
+    p = x360._capi.Params()
+    p.struct_size = 12
+    plan = ctypes.c_void_p()
+    assert lib.x360_plan_create(ctypes.byref(p), ctypes.byref(plan)) == -1
+    assert b"ABI mismatch" in lib.x360_last_error()
+    with pytest.raises(x360.X360Error):
+        x360.Extractor(0, 0, 64, 90, np.eye(3)[None])
+    with pytest.raises(x360.X360Error):
+        x360.Extractor(64, 128, 32, 200.0, np.eye(3)[None])
+
+
+def test_no_cpu_fallback_without_device(x360):
+    """On a box without CUDA every compute entry must fail loudly (never silently compute on the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(x360.X360Error, match="no CUDA device|CUDA"):
+        x360.ImageUtils.calculate_blur_score(np.zeros((8, 8), np.uint8))
+    with pytest.raises(x360.X360Error):
+        x360.Extractor(64, 128, 32, 90, np.eye(3)[None])
+    with pytest.raises(x360.X360Error):
+        x360.remap(np.zeros((8, 8, 3), np.uint8), np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32))
+    assert x360.ImageUtils.calculate_blur_score(None) == 0.0     # image_utils.py:18-19: never raises
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "360extractor_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"(from|import)\s+oracle|oracle[/.]|libx360_oracle", text), f"{f} reaches into oracle/"
+                assert "import cv2" not in text, f"{f} imports cv2"
+
+
+# ---- blur accept / reject machine (processor.py:341-376) --------------------------------------
+def _reference_fsm(scores, enabled, smart, threshold):
+    """Independent transliteration of the decision order for the test (NOT imported by the product)."""
+    from collections import deque
+    hist, skips, keep = deque(maxlen=10), 0, []
+    for s in scores:
+        if not enabled:
+            keep.append(True)
+            continue
+        blurry = False
+        if smart:
+            if s < threshold:
+                blurry = True
+            elif len(hist) > 0 and s < (sum(hist) / len(hist)) * 0.6:
+                blurry = True
+            if blurry:
+                skips += 1
+                if skips > 5:
+                    blurry, skips = False, 0
+            if not blurry:
+                skips = 0
+                hist.append(s)
+        elif s < threshold:
+            blurry = True
+        keep.append(not blurry)
+    return keep
+
+
+@pytest.mark.parametrize("smart", [False, True])
+def test_blur_filter_replay(x360, smart):
+    rng = np.random.default_rng(5)
+    scores = np.concatenate([rng.uniform(50, 400, 40), rng.uniform(0, 90, 12), rng.uniform(300, 900, 20),
+                             rng.uniform(100, 160, 30)])
+    table = scores.reshape(-1, 6)
+    f = x360.BlurFilter(True, smart, 100.0)
+    got = f.replay(table)
+    want = np.array(_reference_fsm(list(scores), True, smart, 100.0)).reshape(-1, 6)
+    assert np.array_equal(np.array(got), want)
+    assert f.skipped == int((~want).sum())
+    if smart:
+        assert f.forced >= 1                      # 12 sub-threshold scores in a row force an accept
+    off = x360.BlurFilter(False, smart, 100.0)
+    assert all(all(r) for r in off.replay(table))
+
+
+def test_blur_filter_from_settings_defaults(x360):
+    f = x360.BlurFilter.from_settings({})
+    assert (f.enabled, f.smart, f.threshold) == (False, False, 100.0)   # processor.py:219-221
+    f = x360.BlurFilter.from_settings({"blur_filter_enabled": True, "smart_blur_enabled": True, "blur_threshold": 42.5})
+    assert (f.enabled, f.smart, f.threshold) == (True, True, 42.5)
