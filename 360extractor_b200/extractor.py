@@ -135,6 +135,15 @@ class Extractor:
 
         frames ``[F][H][W][3]`` uint8, out ``[F][V][d][d][3]`` uint8, sums int64 ``[F][V]`` or None."""
         F = int(frames.shape[0])
+        for name, t, shape in (("frames", frames, (F,) + self.frame_shape), ("out", out, self.views_shape(F)),
+                               ("sum_lap", sum_lap, (F, self.n_views)), ("sum_lap2", sum_lap2, (F, self.n_views))):
+            if t is None:
+                continue
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+            contiguous = t.is_contiguous() if hasattr(t, "is_contiguous") else t.flags.c_contiguous
+            if not contiguous:
+                raise ValueError(f"{name} must be C-contiguous (the C-ABI takes dense [F][H][W][3] / [F][V][d][d][3] buffers)")
         st = None
         if stream is not None:
             st = getattr(stream, "cuda_stream", stream)

@@ -59,4 +59,4 @@ def smooth_frame(seed, h, w):
     x0 = np.floor(xs).astype(int); x1 = np.minimum(x0 + 1, lo.shape[1] - 1); fx = (xs - x0)[None, :, None]
     top = lo[y0][:, x0] * (1 - fx) + lo[y0][:, x1] * fx
     bot = lo[y1][:, x0] * (1 - fx) + lo[y1][:, x1] * fx
-    return np.clip(np.rint(top * (1 - fy) + bot * fy), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(top * (1 - fy) + bot * fy), 0, 255).astype(np.uint8))

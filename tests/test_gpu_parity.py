@@ -151,6 +151,7 @@ def test_device_resident_path(x360, oracle):
         d_s = torch.full((4, 8), -1, dtype=torch.int64, device=dev)
         d_s2 = torch.full((4, 8), -1, dtype=torch.int64, device=dev)
         side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())             # uploads / fills above ran on the current stream
         with torch.cuda.stream(side):
             before = x360.launch_count()
             ex.extract_device(d_frames, d_out, d_s, d_s2, stream=side)
@@ -161,6 +162,10 @@ def test_device_resident_path(x360, oracle):
         ex.extract_device(d_frames, d_out, None, None, stream=torch.cuda.current_stream())
         torch.cuda.synchronize()
         assert_same(d_out.cpu().numpy(), want, "device path, no scores")
+        with pytest.raises(ValueError, match="contiguous"):
+            ex.extract_device(d_frames.transpose(1, 2).contiguous().transpose(1, 2), d_out)
+        with pytest.raises(ValueError, match="shape"):
+            ex.extract_device(d_frames[:, :100], d_out)
 
 
 def test_explicit_map_remap_and_blur_score(x360, oracle):
