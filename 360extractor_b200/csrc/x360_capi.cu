@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -20,6 +21,7 @@
 #include "x360_lanczos.cuh"
 #include "x360_linear.cuh"
 #include "x360_misc.cuh"
+#include "x360_staged.cuh"
 #include "x360_tables.hpp"
 
 using namespace x360;
@@ -76,18 +78,55 @@ int check_dims(int W, int H, int ow, int oh)
 }
 
 typedef void (*extract_fn)(const ExtractArgs);
+typedef void (*staged_fn)(const ExtractArgs, const TmapSet);
 
-struct Variant {
-    extract_fn fn;
-    int min_blocks;
-};
-
-Variant pick_variant(int interp, bool scores)
+// The direct extraction kernel for (interpolation, scores); Lanczos4 has the direct path only.
+extract_fn pick_direct(int interp, bool scores)
 {
     if (interp == X360_INTERP_LANCZOS4)
-        return scores ? Variant{extract_direct<LanczosSampler, true, 2>, 2} : Variant{extract_direct<LanczosSampler, false, 2>, 2};
-    return scores ? Variant{extract_direct<LinearSampler, true, 3>, 3} : Variant{extract_direct<LinearSampler, false, 4>, 4};
+        return scores ? extract_direct<LanczosSampler, true, 2> : extract_direct<LanczosSampler, false, 2>;
+    return scores ? extract_direct<LinearSampler, true, 3> : extract_direct<LinearSampler, false, 4>;
 }
+
+staged_fn pick_staged(bool scores) { return scores ? extract_linear_staged<true> : extract_linear_staged<false>; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked).
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn tensor_map_encoder()
+{
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+// uint8 [F][H][3W] frame tensor, boxes {128 + 32 k bytes, kBoxRows rows, 1 frame}
+bool encode_frame_maps(const uint8_t *frames, int F, int H, int W, TmapSet *out)
+{
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)F};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * H};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int k = 0; k < kNumBoxWidths; ++k) {
+        const cuuint32_t box[3] = {(cuuint32_t)(128 + 32 * k), (cuuint32_t)kBoxRows, 1};
+        if (enc(&out->m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)frames, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
@@ -97,6 +136,10 @@ struct x360_plan {
     int sm_count = 0;
     double *d_R = nullptr;
     int16_t *d_lz = nullptr;
+    int path = X360_PATH_DIRECT;        // resolved path of the extraction kernel
+    int px_max = 0, rows_max = 0, pp = 0, raw_pitch = 0;
+    size_t smem = 0;                     // dynamic shared memory of the staged kernel
+    unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch
     // pipelined host path
     int chunk = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
@@ -108,9 +151,13 @@ struct x360_plan {
 
 static int plan_grid(const x360_plan *pl, bool scores)
 {
-    const Variant v = pick_variant(pl->p.interp, scores);
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    cudaError_t e;
+    if (pl->path == X360_PATH_STAGED)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_staged(scores), kThreads, pl->smem);
+    else
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_direct(pl->p.interp, scores), kThreads, 0);
+    if (e != cudaSuccess || occ < 1) occ = 1;
     const int n_tiles = pl->p.n_views * pl->g.tiles_x * pl->g.tiles_y;
     const int cap = pl->sm_count * occ;
     return n_tiles < cap ? n_tiles : cap;
@@ -143,8 +190,9 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (!(params->fov_deg > 0.0 && params->fov_deg < 180.0)) return fail(X360_E_INVALID, "fov_deg %g outside (0, 180)", params->fov_deg);
     if (params->interp != X360_INTERP_LINEAR && params->interp != X360_INTERP_LANCZOS4)
         return fail(X360_E_INVALID, "unknown interp %d", params->interp);
-    if (params->path != X360_PATH_AUTO && params->path != X360_PATH_DIRECT)
-        return fail(X360_E_UNSUPPORTED, "path %d is not built into this library", params->path);
+    if (params->path < X360_PATH_AUTO || params->path > X360_PATH_STAGED) return fail(X360_E_INVALID, "unknown path %d", params->path);
+    if (params->path == X360_PATH_STAGED && params->interp == X360_INTERP_LANCZOS4)
+        return fail(X360_E_UNSUPPORTED, "the staged path is built for bilinear only; Lanczos4 uses the direct path");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
         return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
@@ -162,7 +210,31 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->g = make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg);
     pl->sm_count = prop.multiProcessorCount;
     pl->chunk = params->max_batch > 0 ? params->max_batch : 8;
+    pl->path = (params->interp == X360_INTERP_LANCZOS4 || params->path == X360_PATH_DIRECT) ? X360_PATH_DIRECT : X360_PATH_STAGED;
+    if (pl->path == X360_PATH_STAGED) {
+        // Footprint capacity: a 34-px tile side (32 + halo) times the source/output scale at the view
+        // centre, with head-room for shear and latitude stretch; anything larger goes direct.
+        const double scale = ((double)params->src_w / (2.0 * 3.14159265358979323846)) / pl->g.f;
+        double factor = 1.4;
+        if (const char *e = getenv("X360_STAGE_FACTOR")) factor = atof(e) > 0.5 ? atof(e) : factor;
+        int cap = round_up((int)std::ceil((kTile + 2) * scale * factor) + 8, 4);
+        cap = cap < 16 ? 16 : (cap > 128 ? 128 : cap);
+        for (;; cap -= 4) {                                   // shrink until two CTAs fit one SM
+            pl->px_max = cap; pl->rows_max = cap; pl->pp = cap + 2; pl->raw_pitch = kMaxBoxBytes;
+            pl->smem = staged_smem_bytes(pl->rows_max, pl->pp);
+            if (pl->smem <= 110 * 1024 || cap <= 16) break;
+        }
+        for (int sc = 0; sc < 2; ++sc) {
+            const cudaError_t ea = cudaFuncSetAttribute(pick_staged(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+            if (ea != cudaSuccess) {
+                delete pl;
+                return fail(X360_E_CUDA, "cannot reserve %zu B of shared memory: %s", pl->smem, cudaGetErrorString(ea));
+            }
+        }
+    }
     cudaError_t e = cudaMalloc(&pl->d_R, sizeof(double) * 9 * params->n_views);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_modes, sizeof(unsigned) * 3);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * 3);
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_R, params->R, sizeof(double) * 9 * params->n_views, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && params->interp == X360_INTERP_LANCZOS4) {
         const std::vector<int16_t> t = lanczos4_q15_table();
@@ -183,6 +255,7 @@ int x360_plan_destroy(x360_plan *pl)
     cudaSetDevice(pl->p.device);
     cudaFree(pl->d_R);
     cudaFree(pl->d_lz);
+    cudaFree(pl->d_modes);
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_frames[i]);
         cudaFree(pl->d_views[i]);
@@ -201,10 +274,19 @@ int x360_plan_destroy(x360_plan *pl)
 int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *block, int32_t *smem_bytes)
 {
     if (!pl) return fail(X360_E_INVALID, "null plan");
-    if (path) *path = X360_PATH_DIRECT;
+    if (path) *path = pl->path;
     if (grid) *grid = plan_grid(pl, false);
     if (block) *block = kThreads;
-    if (smem_bytes) *smem_bytes = (int32_t)sizeof(TileSmem);
+    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem);
+    return X360_OK;
+}
+
+int x360_plan_tile_modes(x360_plan *pl, uint32_t *out3)
+{
+    if (!pl || !out3) return fail(X360_E_INVALID, "null argument");
+    CU(cudaSetDevice(pl->p.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out3, pl->d_modes, sizeof(unsigned) * 3, cudaMemcpyDeviceToHost));
     return X360_OK;
 }
 
@@ -231,13 +313,24 @@ int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, 
     a.n_tiles = pl->p.n_views * pl->g.tiles_x * pl->g.tiles_y;
     a.aligned = ((uintptr_t)frames % 4 == 0) && (pl->g.W % 4 == 0) && ((uintptr_t)out_views % 16 == 0) &&
                 (((size_t)pl->g.ow * 3) % 16 == 0);
+    a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)pl->g.W * 3) % 16 == 0) && pl->g.H >= kBoxRows &&
+                 pl->g.W * 3 >= kMaxBoxBytes;
+    a.rows_max = pl->rows_max; a.px_max = pl->px_max; a.pp = pl->pp; a.raw_pitch = pl->raw_pitch;
+    a.tile_modes = pl->d_modes;
+    CU(cudaMemsetAsync(pl->d_modes, 0, sizeof(unsigned) * 3, st));
     if (scores) {
         CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
-    const Variant v = pick_variant(pl->p.interp, scores);
     const int grid = plan_grid(pl, scores);
-    v.fn<<<grid, kThreads, 0, st>>>(a);
+    if (pl->path == X360_PATH_STAGED) {
+        TmapSet tms;
+        memset(&tms, 0, sizeof tms);
+        if (a.stage_ok && !encode_frame_maps(frames, n_frames, pl->g.H, pl->g.W, &tms)) a.stage_ok = 0;   // every tile goes direct
+        pick_staged(scores)<<<grid, kThreads, pl->smem, st>>>(a, tms);
+    } else {
+        pick_direct(pl->p.interp, scores)<<<grid, kThreads, 0, st>>>(a);
+    }
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;

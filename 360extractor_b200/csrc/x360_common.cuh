@@ -41,6 +41,12 @@ struct ExtractArgs {
     int F, V;
     int n_tiles;                // V * tiles_y * tiles_x
     int aligned;                // 1 if frames/out pointers and pitches allow the vector paths
+    // staged path (x360_staged.cuh): capacity of the shared-memory footprint buffers
+    int stage_ok;               // 1 if frames base / row pitch are 16-B aligned (bulk-copy requirement)
+    int rows_max, px_max;       // footprint rows / source pixels per row that fit
+    int pp;                     // pair-record row pitch in pixels (px_max + 2: 16-B rows, bank skew)
+    int raw_pitch;              // raw row pitch in bytes (multiple of 16)
+    unsigned *tile_modes;       // optional [3] counters: staged / direct-aligned / direct-bytewise tiles
 };
 
 __device__ __forceinline__ int wrap_idx(int p, int len)
@@ -148,21 +154,27 @@ __device__ __forceinline__ void tile_coords(const Geom &g, int t, int &v, int &x
 }
 
 // ---- shared-memory layout of one output tile (+ its gray halo) -------------------
+// Gray tile with a 1-px halo: rows -1..32 as compact 32-B rows (row 0 = top halo), the left and
+// right halo columns kept apart so interior rows stay word-aligned and conflict-free.
+struct GrayTile {
+    uint8_t g[kTile + 2][kTile];
+    uint8_t hl[kTile];
+    uint8_t hr[kTile];
+};
+
 struct TileSmem {
     uint8_t out[2][kTile][kTile * 3];        // double-buffered BGR tile, row = 96 B
-    uint8_t gray[2][kTile + 2][kTile];       // rows -1..32 (row 0 = top halo), compact 32-B rows
-    uint8_t hl[2][kTile];                    // left halo column
-    uint8_t hr[2][kTile];                    // right halo column
+    GrayTile gt[2];
     long long sums[2][2];                    // per-buffer (sum L, sum L^2)
     int special;                             // tile has a wrapped tap -> generic gather
 };
 
 // gray value at tile-local (ly, lx) with ly, lx in [-1, kTile]
-__device__ __forceinline__ int gray_at(const TileSmem &s, int b, int ly, int lx)
+__device__ __forceinline__ int gray_at(const GrayTile &t, int ly, int lx)
 {
-    if (lx < 0) return s.hl[b][ly];
-    if (lx >= kTile) return s.hr[b][ly];
-    return s.gray[b][ly + 1][lx];
+    if (lx < 0) return t.hl[ly];
+    if (lx >= kTile) return t.hr[ly];
+    return t.g[ly + 1][lx];
 }
 
 // Halo pixel of thread `tid` (< 128): 0-31 top, 32-63 bottom, 64-95 left, 96-127 right.
@@ -177,14 +189,14 @@ __device__ __forceinline__ void halo_coords(int tid, int x0, int y0, int &hx, in
     }
 }
 
-__device__ __forceinline__ void halo_store(TileSmem &s, int b, int tid, uint8_t g)
+__device__ __forceinline__ void halo_store(GrayTile &t, int tid, uint8_t g)
 {
     const int k = tid & 31;
     switch (tid >> 5) {
-        case 0: s.gray[b][0][k] = g; break;
-        case 1: s.gray[b][kTile + 1][k] = g; break;
-        case 2: s.hl[b][k] = g; break;
-        default: s.hr[b][k] = g; break;
+        case 0: t.g[0][k] = g; break;
+        case 1: t.g[kTile + 1][k] = g; break;
+        case 2: t.hl[k] = g; break;
+        default: t.hr[k] = g; break;
     }
 }
 
@@ -213,18 +225,18 @@ __device__ __forceinline__ void store_tile(const TileSmem &s, int b, uint8_t *__
 
 // Laplacian sums of the tile in buffer b.  Returns this thread's partial (sum L, sum L^2).
 // full: the tile is entirely inside the image (fast 4-pixels-per-thread dp4a path).
-__device__ __forceinline__ void laplacian_partial(const TileSmem &s, int b, const Geom &g, int x0, int y0,
+__device__ __forceinline__ void laplacian_partial(const GrayTile &t, const Geom &g, int x0, int y0,
                                                   bool full, int tid, int &pl, unsigned &pl2)
 {
     pl = 0;
     pl2 = 0;
     if (full) {
         const int ly = tid >> 3, wx = tid & 7;           // one 4-pixel word per thread
-        const uint32_t C = *reinterpret_cast<const uint32_t *>(&s.gray[b][ly + 1][wx * 4]);
-        uint32_t U = *reinterpret_cast<const uint32_t *>(&s.gray[b][ly][wx * 4]);
-        uint32_t D = *reinterpret_cast<const uint32_t *>(&s.gray[b][ly + 2][wx * 4]);
-        uint32_t l = (wx > 0) ? s.gray[b][ly + 1][wx * 4 - 1] : s.hl[b][ly];
-        uint32_t r = (wx < 7) ? s.gray[b][ly + 1][wx * 4 + 4] : s.hr[b][ly];
+        const uint32_t C = *reinterpret_cast<const uint32_t *>(&t.g[ly + 1][wx * 4]);
+        uint32_t U = *reinterpret_cast<const uint32_t *>(&t.g[ly][wx * 4]);
+        uint32_t D = *reinterpret_cast<const uint32_t *>(&t.g[ly + 2][wx * 4]);
+        uint32_t l = (wx > 0) ? t.g[ly + 1][wx * 4 - 1] : t.hl[ly];
+        uint32_t r = (wx < 7) ? t.g[ly + 1][wx * 4 + 4] : t.hr[ly];
         // reflect-101 at the image border: g[-1] = g[1], g[n] = g[n-2]
         if (y0 + ly == 0) U = D;
         if (y0 + ly == g.oh - 1) D = U;
@@ -251,9 +263,9 @@ __device__ __forceinline__ void laplacian_partial(const TileSmem &s, int b, cons
             const int yd = (y == g.oh - 1) ? ((g.oh > 1) ? g.oh - 2 : 0) : y + 1;
             const int xl = (x == 0) ? ((g.ow > 1) ? 1 : 0) : x - 1;
             const int xr = (x == g.ow - 1) ? ((g.ow > 1) ? g.ow - 2 : 0) : x + 1;
-            const int c = gray_at(s, b, ly, lx);
-            const int L = gray_at(s, b, yu - y0, lx) + gray_at(s, b, yd - y0, lx) +
-                          gray_at(s, b, ly, xl - x0) + gray_at(s, b, ly, xr - x0) - 4 * c;
+            const int c = gray_at(t, ly, lx);
+            const int L = gray_at(t, yu - y0, lx) + gray_at(t, yd - y0, lx) +
+                          gray_at(t, ly, xl - x0) + gray_at(t, ly, xr - x0) - 4 * c;
             pl += L;
             pl2 += (unsigned)(L * L);
         }

@@ -73,18 +73,18 @@ extract_direct(const __grid_constant__ ExtractArgs a)
                     const uint32_t pxl = S::gather_fast(fb, px[k], g, a.lz_tab);
                     uint8_t *o = &s.out[b][warp * kSlots + k][lane * 3];
                     o[0] = (uint8_t)pxl; o[1] = (uint8_t)(pxl >> 8); o[2] = (uint8_t)(pxl >> 16);
-                    if (SCORES) s.gray[b][warp * kSlots + k + 1][lane] = (uint8_t)gray_of(pxl);
+                    if (SCORES) s.gt[b].g[warp * kSlots + k + 1][lane] = (uint8_t)gray_of(pxl);
                 }
-                if (SCORES && hvalid) halo_store(s, b, tid, (uint8_t)gray_of(S::gather_fast(fb, hpx, g, a.lz_tab)));
+                if (SCORES && hvalid) halo_store(s.gt[b], tid, (uint8_t)gray_of(S::gather_fast(fb, hpx, g, a.lz_tab)));
             } else {
 #pragma unroll 1
                 for (int k = 0; k < kSlots; ++k) {
                     const uint32_t pxl = S::gather_generic(fb, px[k], g, a.lz_tab);
                     uint8_t *o = &s.out[b][warp * kSlots + k][lane * 3];
                     o[0] = (uint8_t)pxl; o[1] = (uint8_t)(pxl >> 8); o[2] = (uint8_t)(pxl >> 16);
-                    if (SCORES) s.gray[b][warp * kSlots + k + 1][lane] = (uint8_t)gray_of(pxl);
+                    if (SCORES) s.gt[b].g[warp * kSlots + k + 1][lane] = (uint8_t)gray_of(pxl);
                 }
-                if (SCORES && hvalid) halo_store(s, b, tid, (uint8_t)gray_of(S::gather_generic(fb, hpx, g, a.lz_tab)));
+                if (SCORES && hvalid) halo_store(s.gt[b], tid, (uint8_t)gray_of(S::gather_generic(fb, hpx, g, a.lz_tab)));
             }
             __syncthreads();
             // Everything below reads buffer b only; the next iteration writes buffer b^1, whose
@@ -98,7 +98,7 @@ extract_direct(const __grid_constant__ ExtractArgs a)
                     s.sums[b ^ 1][0] = 0; s.sums[b ^ 1][1] = 0;
                 }
                 int pl; unsigned pl2;
-                laplacian_partial(s, b, g, x0, y0, full, tid, pl, pl2);
+                laplacian_partial(s.gt[b], g, x0, y0, full, tid, pl, pl2);
                 pl = __reduce_add_sync(0xffffffffu, pl);
                 pl2 = __reduce_add_sync(0xffffffffu, pl2);
                 if (lane == 0) {

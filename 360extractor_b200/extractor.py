@@ -93,6 +93,12 @@ class Extractor:
         check(lib().x360_plan_info(self._plan, *[ctypes.byref(v) for v in vals]))
         return {"path": vals[0].value, "grid": vals[1].value, "block": vals[2].value, "smem_bytes": vals[3].value}
 
+    def tile_modes(self):
+        """Tiles of the last launch per gather mode (synchronises): staged / direct-aligned / direct-bytewise."""
+        out = (ctypes.c_uint32 * 3)()
+        check(lib().x360_plan_tile_modes(self._plan, out))
+        return {"staged": int(out[0]), "direct_aligned": int(out[1]), "direct_bytewise": int(out[2])}
+
     # -- the hot path --------------------------------------------------------------------------
     def extract(self, frames, want_scores=False, out=None):
         """frames uint8 ``[F][H][W][3]`` (numpy / pinned numpy) -> ``(views uint8 [F][V][d][d][3], scores)``.

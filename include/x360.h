@@ -143,6 +143,11 @@ int64_t x360_launch_count(void);
 /* which path the plan's extract kernel uses (X360_PATH_*), and its launch geometry */
 int x360_plan_info(const x360_plan *plan, int32_t *path, int32_t *grid, int32_t *block, int32_t *smem_bytes);
 
+/* tiles of the LAST extract launch per gather mode: [0] staged in shared memory,
+ * [1] direct aligned-word gather, [2] direct byte-wise gather (seam / pole / odd geometry).
+ * Synchronises the device. */
+int x360_plan_tile_modes(x360_plan *plan, uint32_t *out3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,18 +86,25 @@ SWEEP = [
 ]
 
 
-@pytest.mark.parametrize("mode,interp", [("linear", 0), ("lanczos", 1)])
+# path: 0 = auto (bilinear: footprint staged in shared memory by bulk async copies), 1 = direct gathers
+@pytest.mark.parametrize("mode,interp,path", [("linear", 0, 0), ("linear", 0, 1), ("lanczos", 1, 0)])
 @pytest.mark.parametrize("cfg", SWEEP)
-def test_sweep_against_oracle(x360, oracle, cfg, mode, interp):
+def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
     H, W, d, fov, layout, n, pitch, F = cfg
     frames = np.stack([noise_frame(100 + i, H, W) for i in range(F)])
     views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout)
     R = rotations(x360, views)
     want, ws, ws2 = oracle.extract(frames, R, d, fov, interp)
-    with x360.Extractor(H, W, d, fov, R, mode) as ex:
+    with x360.Extractor(H, W, d, fov, R, mode, path=path) as ex:
+        assert ex.info()["path"] == (1 if (interp or path == 1) else 2)
         got, s, s2 = ex.extract_sums(frames)
+        modes = ex.tile_modes()
         got_ns, none = ex.extract(frames, want_scores=False)      # the no-score kernel variant
     assert none is None
+    if interp == 0 and path == 0:
+        assert sum(modes.values()) == len(views) * ((d + 31) // 32) ** 2
+        if W % 16 == 0:
+            assert modes["staged"] > 0, modes
     assert_same(got, want, f"{cfg} {mode}", LANCZOS_TOL_LSB if interp else 0)
     assert_same(got_ns, want, f"{cfg} {mode} (no scores)", LANCZOS_TOL_LSB if interp else 0)
     assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
@@ -242,7 +249,10 @@ def test_full_size_configs(x360, oracle, cfg):
     names, R = x360.rotation_stack(views, active)
     with x360.Extractor(H, W, d, fov, R, mode, max_batch=1) as ex:
         got, s, s2 = ex.extract_sums(frames)
+        modes = ex.tile_modes()
         again, s_b, s2_b = ex.extract_sums(frames)
+    if not interp:                                      # most tiles take the staged path; poles / seam fall back
+        assert modes["staged"] > 0.7 * sum(modes.values()), modes
     # size-independent properties: deterministic, every view differs, sums consistent with the pixels
     assert np.array_equal(got, again) and np.array_equal(s, s_b) and np.array_equal(s2, s2_b)
     assert len({sha(got[0, v]) for v in range(len(names))}) == len(names)
