@@ -88,7 +88,14 @@ extract_fn pick_direct(int interp, bool scores)
     return scores ? extract_direct<LinearSampler, true, 3> : extract_direct<LinearSampler, false, 4>;
 }
 
-staged_fn pick_staged(bool scores) { return scores ? extract_linear_staged<true> : extract_linear_staged<false>; }
+// MINB (CTAs per SM the register allocation aims for) is a tuning knob: X360_STAGED_MINB=3 trades
+// occupancy for instruction-level parallelism inside the gather.
+staged_fn pick_staged(bool scores)
+{
+    static const int minb = [] { const char *e = getenv("X360_STAGED_MINB"); return e ? atoi(e) : 4; }();
+    if (minb == 3) return scores ? extract_linear_staged<true, 3> : extract_linear_staged<false, 3>;
+    return scores ? extract_linear_staged<true, 4> : extract_linear_staged<false, 4>;
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked).
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

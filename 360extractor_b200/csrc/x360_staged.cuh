@@ -120,8 +120,8 @@ __device__ __forceinline__ uint32_t sample_staged(const PxState &p, uint32_t row
     return __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x7610);       // [vb.b2, vg.b2, vr.b2, 0]
 }
 
-template <bool SCORES>
-__global__ void __launch_bounds__(kThreads, 4)
+template <bool SCORES, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 extract_linear_staged(const __grid_constant__ ExtractArgs a, const __grid_constant__ TmapSet tms)
 {
     extern __shared__ __align__(128) uint8_t dsm[];

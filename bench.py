@@ -213,7 +213,7 @@ def workload_config(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override frames per step per GPU")
@@ -270,11 +270,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                       # nvidia-smi needs ~100 ms to start: begin before the warm-up
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = pkg.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -286,7 +286,16 @@ def main():
     launches = pkg.launch_count() - launches0
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
+    modes = ex.tile_modes()
+    # keep the SAME steps running (untimed) until the sampler has seen >= 1 s of load: the timed
+    # region alone is a few tens of ms, shorter than one nvidia-smi sampling period
+    soak_t0 = time.perf_counter()
+    while time.perf_counter() - soak_t0 < 1.2:
+        for _ in range(10):
+            ex.extract_device(d_frames, d_out, d_s, d_s2, stream=stream)
+        torch.cuda.synchronize()
     clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps + 1.2 s soak of identical steps (100 ms sampling)"
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,8 +313,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg_frame,
                 "touched_source_pixels_per_frame": U, "bytes_per_output_pixel": b_alg_frame / (V * d * d),
-                "kernel": "extract_direct<%s,%s>" % ("LanczosSampler" if wl["mode"] == "lanczos" else "LinearSampler",
-                                                     "scores" if wl["scores"] else "noscores"),
+                "kernel": ("extract_direct<LanczosSampler,%s>" if wl["mode"] == "lanczos" else
+                           ("extract_linear_staged<%s>" if ex.info()["path"] == 2 else "extract_direct<LinearSampler,%s>"))
+                          % ("scores" if wl["scores"] else "noscores"),
+                "tile_modes": modes,
                 "kernel_ms_mean": kernel_ms, "kernel_ms_min": min(step_ms), "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # ---- end to end through the public host API (pinned host buffers) ----------------------
