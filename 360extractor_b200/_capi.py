@@ -11,7 +11,7 @@ from .build import LIB_PATH
 X360_OK = 0
 INTERP_LINEAR = 0
 INTERP_LANCZOS4 = 1
-PATH_AUTO, PATH_DIRECT, PATH_STAGED = 0, 1, 2
+PATH_AUTO, PATH_DIRECT, PATH_STAGED, PATH_TILED = 0, 1, 2, 3
 
 
 class X360Error(RuntimeError):

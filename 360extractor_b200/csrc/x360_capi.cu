@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,7 @@
 #include "x360_misc.cuh"
 #include "x360_staged.cuh"
 #include "x360_tables.hpp"
+#include "x360_tiled.cuh"
 
 using namespace x360;
 
@@ -135,6 +137,140 @@ bool encode_frame_maps(const uint8_t *frames, int F, int H, int W, TmapSet *out)
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// ---- tiled path (x360_tiled.cuh) ---------------------------------------------------------------
+typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
+
+tiled_fn pick_tiled(bool scores) { return scores ? extract_linear_tiled<true> : extract_linear_tiled<false>; }
+
+// load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W];
+// store box {96, 32, 1} of uint8 [F*V][oh][3 ow]
+bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max, bool with_in, uint8_t *out, int FV, int oh,
+                       int ow, bool with_out, TiledMaps *tm)
+{
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (with_in) {
+        const cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)F};
+        const cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * H};
+        for (int k = 0; k < kTNumBox; ++k) {
+            const int rows = rows_max - kTBoxRows * (kTNumBoxH - 1 - k / kTNumBoxW);
+            const cuuint32_t box[3] = {(cuuint32_t)(48 * (k % kTNumBoxW + 1)), (cuuint32_t)(rows < 8 ? 8 : rows), 1};
+            if (enc(&tm->in[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)frames, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return false;
+        }
+    }
+    if (with_out) {
+        const cuuint64_t dims[3] = {(cuuint64_t)ow * 3, (cuuint64_t)oh, (cuuint64_t)FV};
+        const cuuint64_t strides[2] = {(cuuint64_t)ow * 3, (cuuint64_t)ow * 3 * oh};
+        const cuuint32_t box[3] = {(cuuint32_t)(kTile * 3), (cuuint32_t)kTile, 1};
+        if (enc(&tm->out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)out, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+// Rb = Ry(delta) Ra ?  (the reference's Ry, geometry.py:105-109) -> delta in radians.
+// Ring views and the four horizontal cube faces differ only by such a yaw: map_y is identical and
+// map_x is shifted by delta / 2pi * W.
+bool yaw_delta(const double *Ra, const double *Rb, double *delta)
+{
+    double M[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            M[i][j] = Rb[3 * i] * Ra[3 * j] + Rb[3 * i + 1] * Ra[3 * j + 1] + Rb[3 * i + 2] * Ra[3 * j + 2];
+    const double tol = 1e-12;
+    if (std::fabs(M[1][1] - 1.0) > tol || std::fabs(M[0][1]) > tol || std::fabs(M[1][0]) > tol ||
+        std::fabs(M[1][2]) > tol || std::fabs(M[2][1]) > tol || std::fabs(M[0][0] - M[2][2]) > tol ||
+        std::fabs(M[0][2] + M[2][0]) > tol)
+        return false;
+    *delta = std::atan2(M[0][2], M[0][0]);
+    return true;
+}
+
+struct HostUnits {
+    std::vector<TiledUnit> units;      // largest first
+    std::vector<int> view;
+    std::vector<double> shift;
+};
+
+HostUnits build_units(const double *R, int V, int W, bool share)
+{
+    std::vector<std::vector<int>> members;
+    std::vector<std::vector<double>> shifts;
+    for (int v = 0; v < V; ++v) {
+        bool placed = false;
+        for (size_t u = 0; share && u < members.size() && !placed; ++u) {
+            double d;
+            if ((int)members[u].size() < kTMaxUnitViews && yaw_delta(R + 9 * members[u][0], R + 9 * v, &d)) {
+                double sh = d / (2.0 * 3.14159265358979323846) * (double)W;
+                if (sh < 0.0) sh += (double)W;
+                if (sh >= (double)W) sh = 0.0;
+                members[u].push_back(v);
+                shifts[u].push_back(sh);
+                placed = true;
+            }
+        }
+        if (!placed) {
+            members.push_back({v});
+            shifts.push_back({0.0});
+        }
+    }
+    std::vector<size_t> order(members.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return members[x].size() > members[y].size(); });
+    HostUnits h;
+    for (size_t o : order) {
+        TiledUnit t;
+        t.first = (int)h.view.size();
+        t.n = (int)members[o].size();
+        h.units.push_back(t);
+        h.view.insert(h.view.end(), members[o].begin(), members[o].end());
+        h.shift.insert(h.shift.end(), shifts[o].begin(), shifts[o].end());
+    }
+    return h;
+}
+
+// Host estimate of the per-tile source footprints (9 sample points of each 34x34 tile + halo), to
+// size the staging buffers so that `pct` of the tiles fit: rows and (8-aligned) pixels per row.
+void survey_footprints(const Geom &g, const double *R, int V, double pct, int *rows_out, int *npx_out)
+{
+    std::vector<int> rows, npx;
+    for (int v = 0; v < V; ++v) {
+        const double *Rv = R + 9 * v;
+        for (int ty = 0; ty < g.tiles_y; ++ty)
+            for (int tx = 0; tx < g.tiles_x; ++tx) {
+                int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+                for (int j = 0; j < 3; ++j)
+                    for (int i = 0; i < 3; ++i) {
+                        const double x = std::min<double>(std::max(0, tx * kTile - 1 + i * 33 / 2), g.ow - 1);
+                        const double y = std::min<double>(std::max(0, ty * kTile - 1 + j * 33 / 2), g.oh - 1);
+                        const double xn = (x - g.cx) / g.f, yn = (y - g.cy) / g.f;
+                        const double v0 = xn * Rv[0] + yn * Rv[1] + Rv[2], v1 = xn * Rv[3] + yn * Rv[4] + Rv[5],
+                                     v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
+                        const double u = (std::atan2(v0, v2) / (2.0 * 3.14159265358979323846) + 0.5) * g.W;
+                        const double w = (std::asin(v1 / std::sqrt(v0 * v0 + v1 * v1 + v2 * v2)) / 3.14159265358979323846 + 0.5) * g.H;
+                        const int ix = (int)std::floor(u), iy = (int)std::floor(w);
+                        xmin = std::min(xmin, ix); xmax = std::max(xmax, ix);
+                        ymin = std::min(ymin, iy); ymax = std::max(ymax, iy);
+                    }
+                if (xmax - xmin > g.W / 2) continue;                      // wraps the seam: never staged
+                rows.push_back(ymax - ymin + 3);
+                npx.push_back(xmax - (xmin & ~3) + 2);
+            }
+    }
+    if (rows.empty()) { *rows_out = 16; *npx_out = 48; return; }
+    std::sort(rows.begin(), rows.end());
+    std::sort(npx.begin(), npx.end());
+    const size_t k = std::min(rows.size() - 1, (size_t)(pct * (double)rows.size()));
+    *rows_out = rows[k];
+    *npx_out = npx[k];
+}
+
 }  // namespace
 
 struct x360_plan {
@@ -146,7 +282,13 @@ struct x360_plan {
     int path = X360_PATH_DIRECT;        // resolved path of the extraction kernel
     int px_max = 0, rows_max = 0, pp = 0, raw_pitch = 0;
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
-    unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch
+    unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
+    // tiled path
+    int t_bw = 144, t_rows = 40, n_units = 0;
+    size_t t_smem = 0;
+    TiledUnit *d_units = nullptr;
+    int *d_unit_view = nullptr;
+    double *d_unit_shift = nullptr;
     // pipelined host path
     int chunk = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
@@ -160,7 +302,11 @@ static int plan_grid(const x360_plan *pl, bool scores)
 {
     int occ = 0;
     cudaError_t e;
-    if (pl->path == X360_PATH_STAGED)
+    if (pl->path == X360_PATH_TILED) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores), kTT, pl->t_smem);
+        if (e != cudaSuccess || occ < 1) occ = 1;
+        return pl->sm_count * occ;                 // capped by the item count at launch
+    } else if (pl->path == X360_PATH_STAGED)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_staged(scores), kThreads, pl->smem);
     else
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_direct(pl->p.interp, scores), kThreads, 0);
@@ -168,6 +314,69 @@ static int plan_grid(const x360_plan *pl, bool scores)
     const int n_tiles = pl->p.n_views * pl->g.tiles_x * pl->g.tiles_y;
     const int cap = pl->sm_count * occ;
     return n_tiles < cap ? n_tiles : cap;
+}
+
+static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint8_t *out_views, int64_t *sum_lap,
+                        int64_t *sum_lap2, cudaStream_t st)
+{
+    const bool scores = sum_lap != nullptr;
+    const Geom &g = pl->g;
+    TiledArgs a;
+    memset(&a, 0, sizeof a);
+    a.g = g;
+    a.frames = frames;
+    a.out = out_views;
+    a.sum_lap = (long long *)sum_lap;
+    a.sum_lap2 = (long long *)sum_lap2;
+    a.R = pl->d_R;
+    a.units = pl->d_units;
+    a.unit_view = pl->d_unit_view;
+    a.unit_shift = pl->d_unit_shift;
+    a.counter = pl->d_modes + 3;
+    a.tile_modes = pl->d_modes;
+    a.n_units = pl->n_units;
+    a.F = n_frames;
+    a.V = pl->p.n_views;
+    a.rows_max = pl->t_rows;
+    a.bw_max = pl->t_bw;
+    a.aligned = ((uintptr_t)frames % 4 == 0) && (g.W % 4 == 0);
+    a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= pl->t_rows && g.W * 3 >= 256;
+    a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= kTile;
+    if (getenv("X360_NO_TMA_STORE") && atoi(getenv("X360_NO_TMA_STORE"))) a.store_ok = 0;
+
+    // frames per chunk: enough work items for the dynamic scheduler to balance the grid, but as many
+    // frames per item as possible (the map of a tile is evaluated once per item)
+    const int cap = plan_grid(pl, scores);
+    const long long tiles = (long long)g.tiles_x * g.tiles_y;
+    long long want_chunks = (6LL * cap + pl->n_units * tiles - 1) / (pl->n_units * tiles);
+    if (want_chunks < 1) want_chunks = 1;
+    if (want_chunks > n_frames) want_chunks = n_frames;
+    int FG = (int)((n_frames + want_chunks - 1) / want_chunks);
+    if (const char *e = getenv("X360_FG")) FG = atoi(e) > 0 ? atoi(e) : FG;
+    if (FG > n_frames) FG = n_frames;
+    a.FG = FG;
+    a.n_chunks = (n_frames + FG - 1) / FG;
+    const long long n_items = (long long)pl->n_units * tiles * a.n_chunks;
+    if (n_items > 0x7fffffff) return fail(X360_E_INVALID, "too many work items (%lld)", n_items);
+    a.n_items = (int)n_items;
+
+    TiledMaps tms;
+    memset(&tms, 0, sizeof tms);
+    if ((a.stage_ok || a.store_ok) &&
+        !encode_tiled_maps(frames, n_frames, g.H, g.W, pl->t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, a.store_ok != 0, &tms)) {
+        a.stage_ok = 0;                                   // every tile goes direct, byte stores
+        a.store_ok = 0;
+    }
+    CU(cudaMemsetAsync(pl->d_modes, 0, sizeof(unsigned) * 4, st));
+    if (scores) {
+        CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
+        CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
+    }
+    const int grid = (int)std::min<long long>(n_items, cap);
+    pick_tiled(scores)<<<grid, kTT, pl->t_smem, st>>>(a, tms);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    return X360_OK;
 }
 
 extern "C" {
@@ -197,9 +406,9 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (!(params->fov_deg > 0.0 && params->fov_deg < 180.0)) return fail(X360_E_INVALID, "fov_deg %g outside (0, 180)", params->fov_deg);
     if (params->interp != X360_INTERP_LINEAR && params->interp != X360_INTERP_LANCZOS4)
         return fail(X360_E_INVALID, "unknown interp %d", params->interp);
-    if (params->path < X360_PATH_AUTO || params->path > X360_PATH_STAGED) return fail(X360_E_INVALID, "unknown path %d", params->path);
-    if (params->path == X360_PATH_STAGED && params->interp == X360_INTERP_LANCZOS4)
-        return fail(X360_E_UNSUPPORTED, "the staged path is built for bilinear only; Lanczos4 uses the direct path");
+    if (params->path < X360_PATH_AUTO || params->path > X360_PATH_TILED) return fail(X360_E_INVALID, "unknown path %d", params->path);
+    if ((params->path == X360_PATH_STAGED || params->path == X360_PATH_TILED) && params->interp == X360_INTERP_LANCZOS4)
+        return fail(X360_E_UNSUPPORTED, "the staged and tiled paths are built for bilinear only; Lanczos4 uses the direct path");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
         return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
@@ -217,7 +426,31 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->g = make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg);
     pl->sm_count = prop.multiProcessorCount;
     pl->chunk = params->max_batch > 0 ? params->max_batch : 8;
-    pl->path = (params->interp == X360_INTERP_LANCZOS4 || params->path == X360_PATH_DIRECT) ? X360_PATH_DIRECT : X360_PATH_STAGED;
+    pl->path = (params->interp == X360_INTERP_LANCZOS4 || params->path == X360_PATH_DIRECT) ? X360_PATH_DIRECT
+               : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
+    if (pl->path == X360_PATH_TILED) {
+        // staging capacity from a host survey of the tiles' footprints: X360_STAGE_PCT of them fit
+        double pct = 0.97;
+        if (const char *e = getenv("X360_STAGE_PCT")) pct = atof(e) > 0.0 && atof(e) < 1.0 ? atof(e) : pct;
+        int rows = 0, npx = 0;
+        survey_footprints(pl->g, params->R, params->n_views, pct, &rows, &npx);
+        int bw = (12 + 3 * (npx + 1) + 47) / 48 * 48;              // raw bytes per footprint row, worst alignment
+        bw = bw < 96 ? 96 : (bw > 48 * kTNumBoxW ? 48 * kTNumBoxW : bw);
+        if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
+        rows = round_up(rows < 24 ? 24 : rows, kTBoxRows);
+        if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
+        while (rows > 24 && tiled_smem_bytes(rows, bw) > 100 * 1024) rows -= kTBoxRows;
+        pl->t_bw = bw;
+        pl->t_rows = rows;
+        pl->t_smem = tiled_smem_bytes(rows, bw);
+        for (int sc = 0; sc < 2; ++sc) {
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem);
+            if (ea != cudaSuccess) {
+                delete pl;
+                return fail(X360_E_CUDA, "cannot reserve %zu B of shared memory: %s", pl->t_smem, cudaGetErrorString(ea));
+            }
+        }
+    }
     if (pl->path == X360_PATH_STAGED) {
         // Footprint capacity: a 34-px tile side (32 + halo) times the source/output scale at the view
         // centre, with head-room for shear and latitude stretch; anything larger goes direct.
@@ -240,8 +473,19 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         }
     }
     cudaError_t e = cudaMalloc(&pl->d_R, sizeof(double) * 9 * params->n_views);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_modes, sizeof(unsigned) * 3);
-    if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_modes, sizeof(unsigned) * 4);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * 4);
+    if (e == cudaSuccess && pl->path == X360_PATH_TILED) {
+        const bool share = !(getenv("X360_NO_SHARE") && atoi(getenv("X360_NO_SHARE")));
+        const HostUnits h = build_units(params->R, params->n_views, params->src_w, share);
+        pl->n_units = (int)h.units.size();
+        e = cudaMalloc(&pl->d_units, sizeof(TiledUnit) * h.units.size());
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_view, sizeof(int) * h.view.size());
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_shift, sizeof(double) * h.shift.size());
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_units, h.units.data(), sizeof(TiledUnit) * h.units.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_view, h.view.data(), sizeof(int) * h.view.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_shift, h.shift.data(), sizeof(double) * h.shift.size(), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_R, params->R, sizeof(double) * 9 * params->n_views, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && params->interp == X360_INTERP_LANCZOS4) {
         const std::vector<int16_t> t = lanczos4_q15_table();
@@ -263,6 +507,9 @@ int x360_plan_destroy(x360_plan *pl)
     cudaFree(pl->d_R);
     cudaFree(pl->d_lz);
     cudaFree(pl->d_modes);
+    cudaFree(pl->d_units);
+    cudaFree(pl->d_unit_view);
+    cudaFree(pl->d_unit_shift);
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_frames[i]);
         cudaFree(pl->d_views[i]);
@@ -283,8 +530,9 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (!pl) return fail(X360_E_INVALID, "null plan");
     if (path) *path = pl->path;
     if (grid) *grid = plan_grid(pl, false);
-    if (block) *block = kThreads;
-    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem);
+    if (block) *block = pl->path == X360_PATH_TILED ? kTT : kThreads;
+    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->t_smem
+                                  : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
     return X360_OK;
 }
 
@@ -307,6 +555,7 @@ int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, 
     CU(cudaSetDevice(pl->p.device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const bool scores = sum_lap != nullptr;
+    if (pl->path == X360_PATH_TILED) return launch_tiled(pl, frames, n_frames, out_views, sum_lap, sum_lap2, st);
     ExtractArgs a;
     a.g = pl->g;
     a.frames = frames;

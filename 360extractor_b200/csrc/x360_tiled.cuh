@@ -1,0 +1,453 @@
+// x360_tiled.cuh — bilinear extraction, the bench kernel: TMA in, pair records, dp2a gather, TMA out.
+//
+// Contract: src/core/processor.py:327-342 for a frame batch (cv2.remap INTER_LINEAR + BORDER_WRAP,
+// optional calculate_blur_score), map of src/core/geometry.py:141-190 evaluated on the fly and
+// never stored in HBM.  Differences from x360_staged.cuh (kept as the comparison path) are about
+// instruction and shared-memory traffic per output pixel, not about arithmetic:
+//
+//   work item   = (view unit, 32x32 output tile, frame chunk), handed out by a global atomic
+//                 counter.  A view unit is a set of views whose rotations differ only by a yaw
+//                 (ring layouts, the four horizontal cube faces): their maps are one fp64 map plus
+//                 a per-view shift of map_x, so the atan2/asin evaluation is done once per item
+//                 and shared by all views and frames of the item.
+//   per view    : Q5 coordinates from the shared map (+ shift, in fp64 before the float32
+//                 rounding), bounding box of the 2x2 footprints, per-pixel gather state
+//                 (pair-record address, two packed 16-bit weight pairs): 3 registers per pixel.
+//   per frame   : 1. footprint rows arrive in `raw` by TMA boxes (UTMALDG.3D) on an mbarrier;
+//                 2. transform: 8 source pixels per thread, 24 B of packed BGR -> eight 8-byte
+//                    "pair" records [B(x) B(x+1) G(x) G(x+1)] [R(x) R(x+1) . .], stored as four
+//                    conflict-free STS.128 (records are laid out in 4 planes of 16-byte chunks);
+//                 3. gather: per output pixel 2 LDS.64 + 6 dp2a (weights (32-fy|fy)(32-fx|fx)*64
+//                    as u16 pairs, bias 2^15: the result (V + 512) >> 10 lands in byte 2) + 2 PRMT;
+//                 4. pack: one SHFL + one PRMT turn four lanes' pixels into three BGR words,
+//                    STS.32 into the packed tile, which leaves by ONE TMA store (UTMASTG) per
+//                    tile and frame — no per-row address arithmetic, no store instructions in
+//                    the SM's LSU pipe.
+//
+// Exactness of the u16 weights: w*64 <= 65535 except w00 = 1024 (fx = fy = 0, all other weights
+// 0), which is clamped to 65535: (65535 s + 32768) >> 16 = s for every byte s.  Everything else
+// is the same integer expression as cv2.remap's (sum w s + 2^14) >> 15.
+//
+// Tiles whose footprint wraps the seam, touches a pole, exceeds the staging capacity or whose
+// geometry defeats the TMA alignment rules fall back per (tile, view), inside the same launch, to
+// the aligned-word / byte gathers of LinearSampler.
+#pragma once
+#include <climits>
+#include <cuda.h>
+
+#include "x360_common.cuh"
+#include "x360_linear.cuh"
+#include "x360_staged.cuh"      // mbarrier / TMA load helpers
+
+namespace x360 {
+
+constexpr int kTT = 128;              // threads per CTA: 4 warps, warp w owns tile rows 8w .. 8w+7
+constexpr int kTP = 8;                // output pixels (rows) per thread
+constexpr int kTBoxRows = 8;          // granularity of the footprint row capacity
+constexpr int kTNumBoxW = 5;          // load box widths 48, 96, 144, 192, 240 bytes (16, 32, ... source pixels)
+constexpr int kTNumBoxH = 3;          // load box heights rows_max - 16, rows_max - 8, rows_max
+constexpr int kTNumBox = kTNumBoxW * kTNumBoxH;
+constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
+
+struct TiledMaps {
+    CUtensorMap in[kTNumBox];         // uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]
+    CUtensorMap out;                  // uint8 [F*V][oh][3 ow], box {96, 32, 1}
+};
+
+// One view unit: `n` views starting at `first` in the (view id, shift) tables share a map.
+struct TiledUnit {
+    int first, n;
+};
+
+struct TiledArgs {
+    Geom g;
+    const uint8_t *frames;            // [F][H][W][3]
+    uint8_t *out;                     // [F][V][oh][ow][3]
+    long long *sum_lap, *sum_lap2;    // [F][V] or nullptr
+    const double *R;                  // [V][9]
+    const TiledUnit *units;           // [n_units], largest units first
+    const int *unit_view;             // view index per table entry
+    const double *unit_shift;         // map_x shift (source pixels, in [0, W)) per table entry
+    unsigned *counter;                // work-item counter (zeroed before the launch)
+    unsigned *tile_modes;             // [3] or nullptr
+    int n_units, n_items;
+    int F, V, FG, n_chunks;           // frames, views, frames per chunk, chunks
+    int aligned;                      // direct gathers may use aligned words
+    int stage_ok;                     // TMA loads possible (frame base and pitch 16-B aligned)
+    int store_ok;                     // TMA stores possible (out base and pitch 16-B aligned)
+    int rows_max, bw_max;             // staging capacity: footprint rows, raw bytes per footprint row (48 k)
+};
+
+struct TiledCtrl {
+    int wbb[4][4];                    // per-warp footprint bounding boxes (16-B aligned rows)
+    unsigned long long mbar;
+    long long sums[2];
+    int item;
+};
+
+// Dynamic shared memory, fixed offsets first so every hot address is base + constant:
+//   ctrl | 2 packed BGR tiles | fp64 map_x | Q5 map_y | gray tile | raw (one TMA box) | pair records
+//
+// raw:   `rows` footprint rows of bw = 48 m bytes, dense, so that 4-pixel groups (12 B) tile it without
+//        a seam between rows: group i of the flat sequence starts at delta + 12 i.
+// pairs: group i -> 32 B (records of its 4 pixels) at 32 i + 16 (i >> 2): a 16-B pad after every 16
+//        records makes the transform's STS.128 (lane stride 32 B) conflict-free while 16 consecutive
+//        records stay within 144 B for the gather's LDS.64.  Record x of footprint row r lives at
+//        r * 3 bw + (x >> 4) * 144 + (x & 15) * 8.
+constexpr uint32_t kOffCtl = 0;
+constexpr uint32_t kOffTile = 128;
+constexpr uint32_t kOffU0 = kOffTile + 2 * kTile * kTile * 3;
+constexpr uint32_t kOffSy = kOffU0 + kTile * kTile * 8;
+constexpr uint32_t kOffGray = kOffSy + kTile * kTile * 4;
+constexpr uint32_t kOffRaw = (kOffGray + (uint32_t)sizeof(GrayTile) + 127u) & ~127u;
+static_assert(sizeof(TiledCtrl) <= 128, "ctrl block");
+
+__host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 128u + 127u) & ~127u; }
+__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max)
+{
+    return (size_t)kOffRaw + tiled_raw_bytes(rows_max, bw_max) + (size_t)rows_max * 3 * bw_max + 256;
+}
+
+// geometry.py:149-186 for one output pixel: fp64 map_x (unrounded) and float32 map_y.
+__device__ __forceinline__ void map_base(const double *__restrict__ R, const Geom &g, int x, int y, double &uf, float &my)
+{
+    const double xn = __ddiv_rn((double)x - g.cx, g.f);
+    const double yn = __ddiv_rn((double)y - g.cy, g.f);
+    const double v0 = __dadd_rn(__fma_rn(yn, R[1], __dmul_rn(xn, R[0])), R[2]);
+    const double v1 = __dadd_rn(__fma_rn(yn, R[4], __dmul_rn(xn, R[3])), R[5]);
+    const double v2 = __dadd_rn(__fma_rn(yn, R[7], __dmul_rn(xn, R[6])), R[8]);
+    const double theta = atan2(v0, v2);
+    const double rr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)), __dmul_rn(v2, v2)));
+    const double phi = asin(__ddiv_rn(v1, rr));
+    uf = __dmul_rn(__dadd_rn(__ddiv_rn(theta, kTwoPi), 0.5), (double)g.W);
+    my = __double2float_rn(__dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H));
+}
+
+__device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a16x2, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_u(uint32_t a16x2, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b), "r"(c));
+    return d;
+}
+
+// 6 dp2a + 2 PRMT on the two pair records (upper / lower source row): the packed pixel [B, G, R, 0]
+__device__ __forceinline__ uint32_t combine_pairs(uint2 r0, uint2 r1, uint32_t wA, uint32_t wB)
+{
+    const uint32_t vb = dp2a_lo_u(wB, r1.x, dp2a_lo_u(wA, r0.x, 32768u));
+    const uint32_t vg = dp2a_hi_u(wB, r1.x, dp2a_hi_u(wA, r0.x, 32768u));
+    const uint32_t vr = dp2a_lo_u(wB, r1.y, dp2a_lo_u(wA, r0.y, 32768u));
+    return __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x7610);
+}
+
+// pair-record words of source pixel J of a 4-pixel group from its packed BGR words w[0..3]
+template <int J> __device__ __forceinline__ uint32_t pair_lo(const uint32_t (&w)[4])
+{
+    constexpr int n = 3 * J, w0 = n >> 2, r = n - 4 * w0;           // bytes n, n+3, n+1, n+4
+    constexpr uint32_t sel = (uint32_t)r | ((uint32_t)(r + 3) << 4) | ((uint32_t)(r + 1) << 8) | ((uint32_t)(r + 4) << 12);
+    return __byte_perm(w[w0], w[w0 + 1], sel);
+}
+template <int J> __device__ __forceinline__ uint32_t pair_hi(const uint32_t (&w)[4])
+{
+    constexpr int n = 3 * J + 2, w0 = n >> 2, r = n - 4 * w0;       // bytes n, n+3
+    constexpr uint32_t sel = (uint32_t)r | ((uint32_t)(r + 3) << 4);
+    return __byte_perm(w[w0], w[(w0 + 1) < 4 ? w0 + 1 : 3], sel);
+}
+
+// 12 (+3) raw bytes at `src` -> the 4 pair records of one group, 32 B at dst
+__device__ __forceinline__ void transform_group(const uint8_t *src, uint8_t *dst)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint32_t *>(src + 4 * i);
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(pair_lo<0>(w), pair_hi<0>(w), pair_lo<1>(w), pair_hi<1>(w));
+    *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(pair_lo<2>(w), pair_hi<2>(w), pair_lo<3>(w), pair_hi<3>(w));
+}
+
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t src_smem, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tm), "r"(x), "r"(y), "r"(z), "r"(src_smem) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool SCORES>
+__global__ void __launch_bounds__(kTT, SCORES ? 4 : 5)
+extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
+{
+    extern __shared__ __align__(128) uint8_t dsm[];
+    const Geom &g = a.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t pitch = (uint32_t)g.W * 3u;
+    const size_t frame_bytes = (size_t)g.H * pitch;
+    const size_t view_bytes = (size_t)g.oh * g.ow * 3;
+    const size_t opitch = (size_t)g.ow * 3;
+
+    TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
+    uint8_t *const otile = dsm + kOffTile;
+    double *const u0s = reinterpret_cast<double *>(dsm + kOffU0);
+    int *const sy_s = reinterpret_cast<int *>(dsm + kOffSy);
+    GrayTile &gt = *reinterpret_cast<GrayTile *>(dsm + kOffGray);
+    const uint32_t off_pairs = kOffRaw + tiled_raw_bytes(a.rows_max, a.bw_max);     // dsm-relative
+    const uint32_t dsm_s = smem_u32(dsm);
+    const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
+
+    if (tid == 0) mbar_init(&ctl.mbar, 1);
+    uint32_t phase = 0;
+    uint32_t it = 0;                  // frames processed by this CTA: selects the packed-tile buffer
+
+    // frame-invariant: where this lane's packed word of row k goes (+ k * 96), and how it is built
+    const int q = lane & 3;
+    uint32_t pack_sel = q == 0 ? 0x4210u : (q == 1 ? 0x5421u : 0x6542u);
+    uint32_t my_word = (uint32_t)(warp * kTP) * (kTile * 3) + (uint32_t)((lane >> 2) * 3 + q) * 4u;
+    asm volatile("" : "+r"(pack_sel), "+r"(my_word));      // keep both in registers: rematerialising them costs more than the gather
+    const int tiles_per_view = g.tiles_x * g.tiles_y;
+    const double Wd = (double)g.W;
+
+    for (;;) {
+        __syncthreads();                                   // previous item's shared state is dead
+        if (tid == 0) ctl.item = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int item = ctl.item;
+        if (item >= a.n_items) break;
+        const int per_unit = tiles_per_view * a.n_chunks;      // every unit has the same number of items
+        const int u = item / per_unit, local = item - u * per_unit;
+        const TiledUnit unit = a.units[u];
+        const int chunk = local / tiles_per_view, tile = local - chunk * tiles_per_view;
+        const int ty = tile / g.tiles_x;
+        const int x0 = (tile - ty * g.tiles_x) * kTile, y0 = ty * kTile;
+        const int f_begin = chunk * a.FG, f_end = min(a.F, f_begin + a.FG);
+        const bool full = (x0 + kTile <= g.ow) && (y0 + kTile <= g.oh);
+
+        // ---- 1. the unit's map for this tile, to shared memory: fp64 map_x, Q5 map_y -------------
+        double hu0 = 0.0;
+        int hsy = 0;
+        bool hvalid = false;
+        {
+            const double *R = a.R + 9 * a.unit_view[unit.first];
+            const int x = min(x0 + lane, g.ow - 1);
+#pragma unroll 1
+            for (int k = 0; k < kTP; ++k) {
+                double uf; float my;
+                map_base(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), uf, my);
+                u0s[k * kTT + tid] = uf;
+                sy_s[k * kTT + tid] = q5_of(my);
+            }
+            if (SCORES) {
+                int hx, hy;
+                halo_coords(tid, x0, y0, hx, hy);
+                hvalid = (hx >= 0 && hx < g.ow && hy >= 0 && hy < g.oh);
+                if (hvalid) {
+                    float my;
+                    map_base(R, g, hx, hy, hu0, my);
+                    hsy = q5_of(my);
+                }
+            }
+        }
+
+        for (int vi = 0; vi < unit.n; ++vi) {
+            const int v = a.unit_view[unit.first + vi];
+            const double shift = a.unit_shift[unit.first + vi];
+
+            // ---- 2. this view's Q5 coordinates and the footprint bounding box ----------------
+            constexpr int NS = SCORES ? kTP + 1 : kTP;
+            int sxs[kTP + 1], sys[kTP + 1];
+#pragma unroll
+            for (int k = 0; k < kTP; ++k) {
+                double uu = u0s[k * kTT + tid] + shift;
+                if (uu > Wd) uu -= Wd;
+                sxs[k] = q5_of(__double2float_rn(uu));
+                sys[k] = sy_s[k * kTT + tid];
+            }
+            sxs[kTP] = sxs[0];
+            sys[kTP] = sys[0];
+            if (SCORES && hvalid) {
+                double uu = hu0 + shift;
+                if (uu > Wd) uu -= Wd;
+                sxs[kTP] = q5_of(__double2float_rn(uu));
+                sys[kTP] = hsy;
+            }
+            int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int ix = sxs[k] >> 5, iy = sys[k] >> 5;
+                xmin = min(xmin, ix); xmax = max(xmax, ix);
+                ymin = min(ymin, iy); ymax = max(ymax, iy);
+            }
+            xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+            ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+            if (lane == 0) *reinterpret_cast<int4 *>(ctl.wbb[warp]) = make_int4(xmin, xmax, ymin, ymax);
+            if (tid == 0) { ctl.sums[0] = 0; ctl.sums[1] = 0; }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int4 b = *reinterpret_cast<const int4 *>(ctl.wbb[w]);
+                xmin = min(xmin, b.x); xmax = max(xmax, b.y); ymin = min(ymin, b.z); ymax = max(ymax, b.w);
+            }
+
+            // footprint: pair records for x in [x_org, xmax], source rows [ymin, ymax + 1]
+            const int x_org = xmin & ~3, y_org = ymin;
+            const int npx = xmax - x_org + 1, rows = ymax + 2 - ymin;
+            const int gx0 = (3 * x_org) & ~15;                           // TMA: 16-byte aligned byte column
+            const int delta = 3 * x_org - gx0;                           // 0, 4, 8 or 12
+            const int need = delta + 3 * (npx + 1);                      // bytes of a row the records depend on
+            const int wsel = (need + 47) / 48 - 1;                       // box width 48 (wsel + 1)
+            const uint32_t bw = 48u * (uint32_t)(wsel + 1);
+            // one TMA box per frame: the smallest of the three box heights that covers the footprint
+            const int hsel = max(0, kTNumBoxH - 1 - (a.rows_max - rows) / kTBoxRows);
+            const uint32_t box_rows = (uint32_t)(a.rows_max - kTBoxRows * (kTNumBoxH - 1 - hsel));
+            // (coordinates outside [0, W-2] x [0, H-2] mean a wrapped tap: seam or pole)
+            const bool staged = a.stage_ok && xmin >= 0 && ymin >= 0 && xmax <= g.W - 2 && ymax <= g.H - 2 &&
+                                rows <= a.rows_max && bw <= (uint32_t)a.bw_max;
+            bool generic = !a.aligned;
+            if (!staged) {                                               // uniform over the CTA
+                bool special = false;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const int wx0 = wrap_idx(sat_s16(sxs[k] >> 5), g.W), wy0 = wrap_idx(sat_s16(sys[k] >> 5), g.H);
+                    const uint32_t off = (uint32_t)(wy0 * g.W + wx0) * 3u;
+                    special |= (wx0 == g.W - 1) | (wy0 == g.H - 1) | ((off & ~3u) + pitch + 12u > (uint32_t)g.H * pitch);
+                }
+                generic = (__syncthreads_or(special) != 0) || !a.aligned;
+            }
+            if (a.tile_modes && tid == 0 && chunk == 0) atomicAdd(&a.tile_modes[staged ? 0 : (generic ? 2 : 1)], 1u);
+
+            // ---- 3. per-pixel gather state: staged {upper record, lower record, w0x, w1x}, direct {off, wx, wy} --
+            const uint32_t ppitch = 3u * bw;
+            uint32_t pa[kTP + 1], pa2[kTP + 1], pb[kTP + 1], pc[kTP + 1];
+            pa[kTP] = pa2[kTP] = pb[kTP] = pc[kTP] = 0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                if (staged) {
+                    const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
+                    const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
+                    pa[k] = off_pairs + ry * ppitch + (rx >> 4) * 144u + (rx & 15u) * 8u;
+                    pa2[k] = pa[k] + ppitch;
+                    const uint32_t ax0 = 32u - fx, ay0 = (32u - fy) * 64u, ay1 = fy * 64u;
+                    pb[k] = min(ay0 * ax0, 65535u) | ((ay0 * fx) << 16);
+                    pc[k] = (ay1 * ax0) | ((ay1 * fx) << 16);
+                } else {
+                    bool dummy = false;
+                    const LinearSampler::Px d = LinearSampler::make_px(sxs[k], sys[k], g, nullptr, dummy);
+                    pa[k] = d.off; pa2[k] = 0; pb[k] = d.wx; pc[k] = d.wy;
+                }
+            }
+
+            // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
+            const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
+            const uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;
+            const uint32_t tdst0 = off_pairs + 32u * tid + 16u * (tid >> 2);
+            const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
+            auto issue_box = [&](int f) {                                // one thread
+                mbar_arrive_expect_tx(&ctl.mbar, box_rows * bw);
+                tma_load_box(raw_s, tm, gx0, y_org, f, &ctl.mbar);
+            };
+            if (staged && tid == 0) issue_box(f_begin);
+
+            // ---- 4. walk the frame chunk ---------------------------------------------------------
+            const uint8_t *fb = a.frames + (size_t)f_begin * frame_bytes;
+            for (int f = f_begin; f < f_end; ++f, fb += frame_bytes, ++it) {
+                const uint32_t ob = (it & 1u) * (kTile * kTile * 3);
+                if (staged) {
+                    mbar_wait(&ctl.mbar, phase);
+                    phase ^= 1u;
+                    uint32_t src = tsrc0, dst = tdst0;
+#pragma unroll 2
+                    for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 36u * kTT)
+                        transform_group(dsm + src, dsm + dst);
+                }
+                // the TMA store that last read this frame's tile buffer (two frames ago) must be done
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncthreads();                      // pairs ready, raw consumed, tile buffer free
+                if (SCORES && tid == 0 && f > f_begin) {
+                    atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f - 1) * a.V + v], (unsigned long long)ctl.sums[0]);
+                    atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f - 1) * a.V + v], (unsigned long long)ctl.sums[1]);
+                    ctl.sums[0] = 0; ctl.sums[1] = 0;
+                }
+                uint32_t obase = kOffTile + ob + my_word;
+                asm volatile("" : "+r"(obase));
+                uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
+                if (staged) {
+                    if (f + 1 < f_end && tid == 32) issue_box(f + 1);
+#pragma unroll
+                    for (int h = 0; h < kTP; h += 4) {
+                        uint2 r0[4], r1[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            r0[k] = *reinterpret_cast<const uint2 *>(dsm + pa[h + k]);
+                            r1[k] = *reinterpret_cast<const uint2 *>(dsm + pa2[h + k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t pxl = combine_pairs(r0[k], r1[k], pb[h + k], pc[h + k]);
+                            const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
+                            if (q != 3) orow[(h + k) * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
+                            if (SCORES) gt.g[warp * kTP + h + k + 1][lane] = (uint8_t)gray_of(pxl);
+                        }
+                    }
+                    if (SCORES && hvalid) {
+                        const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + pa[kTP]);
+                        const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + pa2[kTP]);
+                        halo_store(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kTP; ++k) {
+                        const LinearSampler::Px d = {pa[k], pb[k], pc[k]};
+                        const uint32_t pxl = generic ? LinearSampler::gather_generic(fb, d, g, nullptr)
+                                                     : LinearSampler::gather_fast(fb, d, g, nullptr);
+                        const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
+                        if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
+                        if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
+                    }
+                    if (SCORES && hvalid) {
+                        const LinearSampler::Px d = {pa[kTP], pb[kTP], pc[kTP]};
+                        halo_store(gt, tid, (uint8_t)gray_of(generic ? LinearSampler::gather_generic(fb, d, g, nullptr)
+                                                                      : LinearSampler::gather_fast(fb, d, g, nullptr)));
+                    }
+                }
+                if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();                      // tile (+ gray halo) complete; pairs free for the next frame
+
+                if (a.store_ok) {
+                    if (tid == 0) tma_store_tile(&tms.out, otile_s + ob, x0 * 3, y0, f * a.V + v);
+                } else {
+                    const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(kTile, g.oh - y0);
+                    uint8_t *out_view = a.out + ((size_t)f * a.V + v) * view_bytes;
+                    for (int i = tid; i < kTile * kTile * 3; i += kTT) {
+                        const int row = i / (kTile * 3), bb = i - row * (kTile * 3);
+                        if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = otile[ob + i];
+                    }
+                }
+                if (SCORES) {
+                    int pl = 0; unsigned pl2 = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int l1; unsigned l2;
+                        laplacian_partial(gt, g, x0, y0, full, tid + h * kTT, l1, l2);
+                        pl += l1; pl2 += l2;
+                    }
+                    pl = __reduce_add_sync(0xffffffffu, pl);
+                    pl2 = __reduce_add_sync(0xffffffffu, pl2);
+                    if (lane == 0) {
+                        atomicAdd((unsigned long long *)&ctl.sums[0], (unsigned long long)(long long)pl);
+                        atomicAdd((unsigned long long *)&ctl.sums[1], (unsigned long long)pl2);
+                    }
+                }
+            }
+            __syncthreads();                           // every warp's partial of the last frame is in
+            if (SCORES && tid == 0) {
+                atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f_end - 1) * a.V + v], (unsigned long long)ctl.sums[0]);
+                atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f_end - 1) * a.V + v], (unsigned long long)ctl.sums[1]);
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace x360

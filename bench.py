@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="skip e2e and cpu baseline (for ncu runs)")
+    ap.add_argument("--path", type=int, default=0, help="x360 kernel path: 0 auto, 1 direct, 2 staged, 3 tiled")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.frames > 0:
@@ -248,7 +249,7 @@ def main():
     views = pkg.GeometryProcessor.generate_views(wl["n"], pitch_offset=wl["pitch"], layout_mode=wl["layout"])
     names, R = pkg.rotation_stack(views, wl["active"])
     V = len(names)
-    ex = pkg.Extractor(H, W, d, wl["fov"], R, wl["mode"], device=local_rank, max_batch=8)
+    ex = pkg.Extractor(H, W, d, wl["fov"], R, wl["mode"], device=local_rank, max_batch=8, path=args.path)
 
     # ---- device-resident batch -------------------------------------------------------------
     host_frames = synth_frames(F, H, W)
@@ -314,7 +315,7 @@ def main():
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg_frame,
                 "touched_source_pixels_per_frame": U, "bytes_per_output_pixel": b_alg_frame / (V * d * d),
                 "kernel": ("extract_direct<LanczosSampler,%s>" if wl["mode"] == "lanczos" else
-                           ("extract_linear_staged<%s>" if ex.info()["path"] == 2 else "extract_direct<LinearSampler,%s>"))
+                           {3: "extract_linear_tiled<%s>", 2: "extract_linear_staged<%s>"}.get(ex.info()["path"], "extract_direct<LinearSampler,%s>"))
                           % ("scores" if wl["scores"] else "noscores"),
                 "tile_modes": modes,
                 "kernel_ms_mean": kernel_ms, "kernel_ms_min": min(step_ms), "frac_of_nominal_8TBs": achieved / 8000.0}

@@ -43,6 +43,8 @@ extern "C" {
 #define X360_PATH_AUTO    0
 #define X360_PATH_DIRECT  1   /* taps gathered straight from global/L2 through L1 */
 #define X360_PATH_STAGED  2   /* per-tile source footprint staged in shared memory by bulk async copies */
+#define X360_PATH_TILED   3   /* TMA in / pair records / dp2a gather / TMA out, maps shared across yaw-shifted views
+                                 (bilinear; what AUTO resolves to) */
 
 typedef struct x360_plan x360_plan;
 

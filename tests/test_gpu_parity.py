@@ -86,8 +86,8 @@ SWEEP = [
 ]
 
 
-# path: 0 = auto (bilinear: footprint staged in shared memory by bulk async copies), 1 = direct gathers
-@pytest.mark.parametrize("mode,interp,path", [("linear", 0, 0), ("linear", 0, 1), ("lanczos", 1, 0)])
+# path: 0 = auto (bilinear: the tiled TMA kernel), 1 = direct gathers, 2 = the earlier staged kernel
+@pytest.mark.parametrize("mode,interp,path", [("linear", 0, 0), ("linear", 0, 1), ("linear", 0, 2), ("lanczos", 1, 0)])
 @pytest.mark.parametrize("cfg", SWEEP)
 def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
     H, W, d, fov, layout, n, pitch, F = cfg
@@ -96,14 +96,15 @@ def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
     R = rotations(x360, views)
     want, ws, ws2 = oracle.extract(frames, R, d, fov, interp)
     with x360.Extractor(H, W, d, fov, R, mode, path=path) as ex:
-        assert ex.info()["path"] == (1 if (interp or path == 1) else 2)
+        assert ex.info()["path"] == (1 if (interp or path == 1) else (2 if path == 2 else 3))
         got, s, s2 = ex.extract_sums(frames)
         modes = ex.tile_modes()
         got_ns, none = ex.extract(frames, want_scores=False)      # the no-score kernel variant
     assert none is None
-    if interp == 0 and path == 0:
+    if interp == 0 and path in (0, 2):
         assert sum(modes.values()) == len(views) * ((d + 31) // 32) ** 2
-        if W % 16 == 0:
+        scale = (W / (2 * np.pi)) / ((d / 2) / np.tan(np.radians(fov) / 2))     # source px per output px at the centre
+        if W % 16 == 0 and scale < 2.0:                  # larger footprints than the staging buffers hold go direct
             assert modes["staged"] > 0, modes
     assert_same(got, want, f"{cfg} {mode}", LANCZOS_TOL_LSB if interp else 0)
     assert_same(got_ns, want, f"{cfg} {mode} (no scores)", LANCZOS_TOL_LSB if interp else 0)
@@ -232,9 +233,9 @@ def test_session_mirrors_processor_loop(x360, oracle):
 FULL = [
     # name, (H, W), layout, n, pitch, active, d, fov, mode, F, views to check against the oracle
     ("cfg1", (1920, 3840), "cube", 6, 0, None, 1024, 90, "linear", 1, [0, 2, 4, 5]),
-    ("cfg2", (2880, 5760), "ring", 8, 0, None, 1600, 90, "linear", 2, [0, 4]),
+    ("cfg2", (2880, 5760), "ring", 8, 0, None, 1600, 90, "linear", 2, [0, 1, 2, 3, 4, 5, 6, 7]),   # all views: one shared map
     ("cfg3", (3840, 7680), "fibonacci", 20, -20, None, 1920, 90, "lanczos", 1, [0, 11]),
-    ("cfg4", (3840, 7680), "cube", 6, 0, None, 1920, 90, "linear", 2, [2, 4]),
+    ("cfg4", (3840, 7680), "cube", 6, 0, None, 1920, 90, "linear", 2, [0, 1, 2, 3, 4, 5]),
     ("cfg5", (5760, 11520), "ring", 12, 0, [0, 3, 6, 9], 2048, 90, "lanczos", 1, [2]),
 ]
 
