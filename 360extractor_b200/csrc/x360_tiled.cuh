@@ -145,6 +145,22 @@ __device__ __forceinline__ uint32_t combine_pairs(uint2 r0, uint2 r1, uint32_t w
     return __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x7610);
 }
 
+// One step down an output column: (X, Y) are the upper / lower pair records of the previous pixel.
+// Mode bits of pixel K in pm: bit 2K = the lower record becomes the upper one and a new lower record is
+// loaded; bit 2K+1 = the upper record is loaded too.  Predicated-off loads cost no shared-memory
+// bandwidth, which is what bounds this kernel.
+template <int K> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y, uint32_t a_upper, uint32_t a_lower, uint32_t pm)
+{
+    asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %6, %7;\n\tsetp.ne.u32 pA, t, 0;\n\t"
+                 "and.b32 t, %6, %8;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                 "@pB mov.b32 %0, %2;\n\t@pB mov.b32 %1, %3;\n\t"
+                 "@pB ld.shared.v2.u32 {%2, %3}, [%5];\n\t"
+                 "@pA ld.shared.v2.u32 {%0, %1}, [%4];\n\t}"
+                 : "+r"(X.x), "+r"(X.y), "+r"(Y.x), "+r"(Y.y)
+                 : "r"(a_upper), "r"(a_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
+}
+
 // pair-record words of source pixel J of a 4-pixel group from its packed BGR words w[0..3]
 template <int J> __device__ __forceinline__ uint32_t pair_lo(const uint32_t (&w)[4])
 {
@@ -326,7 +342,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 if (staged) {
                     const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
                     const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
-                    pa[k] = off_pairs + ry * ppitch + (rx >> 4) * 144u + (rx & 15u) * 8u;
+                    pa[k] = dsm_s + off_pairs + ry * ppitch + (rx >> 4) * 144u + (rx & 15u) * 8u;   // shared-window address
                     pa2[k] = pa[k] + ppitch;
                     const uint32_t ax0 = 32u - fx, ay0 = (32u - fy) * 64u, ay1 = fy * 64u;
                     pb[k] = min(ay0 * ax0, 65535u) | ((ay0 * fx) << 16);
@@ -338,10 +354,22 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 }
             }
 
+            // vertical reuse: a thread walks down one output column, so consecutive pixels usually share
+            // a pair record (same source column; source row the same or one further down).  Two bits
+            // per pixel: 0 keep both records, 1 lower record becomes the upper one (load one), 2 load both.
+            uint32_t pm = 3u;
+#pragma unroll
+            for (int k = 1; k < kTP; ++k) {
+                const bool same = (sxs[k] >> 5) == (sxs[k - 1] >> 5);
+                const int adv = (sys[k] >> 5) - (sys[k - 1] >> 5);
+                pm |= ((same && adv == 0) ? 0u : ((same && adv == 1) ? 1u : 3u)) << (2 * k);
+            }
+
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
             const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
-            const uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;
-            const uint32_t tdst0 = off_pairs + 32u * tid + 16u * (tid >> 2);
+            uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;
+            uint32_t tdst0 = off_pairs + 32u * tid + 16u * (tid >> 2);
+            asm volatile("" : "+r"(tsrc0), "+r"(tdst0));                 // hoisted out of the frame loop for good
             const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
             auto issue_box = [&](int f) {                                // one thread
                 mbar_arrive_expect_tx(&ctl.mbar, box_rows * bw);
@@ -374,25 +402,24 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
                 if (staged) {
                     if (f + 1 < f_end && tid == 32) issue_box(f + 1);
-#pragma unroll
-                    for (int h = 0; h < kTP; h += 4) {
-                        uint2 r0[4], r1[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            r0[k] = *reinterpret_cast<const uint2 *>(dsm + pa[h + k]);
-                            r1[k] = *reinterpret_cast<const uint2 *>(dsm + pa2[h + k]);
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t pxl = combine_pairs(r0[k], r1[k], pb[h + k], pc[h + k]);
-                            const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
-                            if (q != 3) orow[(h + k) * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
-                            if (SCORES) gt.g[warp * kTP + h + k + 1][lane] = (uint8_t)gray_of(pxl);
-                        }
-                    }
+                    uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u);          // upper / lower pair record, carried down the column
+                    auto emit = [&](int k) {
+                        const uint32_t pxl = combine_pairs(X, Y, pb[k], pc[k]);
+                        const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
+                        if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
+                        if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
+                    };
+                    step_records<0>(X, Y, pa[0], pa2[0], pm); emit(0);
+                    step_records<1>(X, Y, pa[1], pa2[1], pm); emit(1);
+                    step_records<2>(X, Y, pa[2], pa2[2], pm); emit(2);
+                    step_records<3>(X, Y, pa[3], pa2[3], pm); emit(3);
+                    step_records<4>(X, Y, pa[4], pa2[4], pm); emit(4);
+                    step_records<5>(X, Y, pa[5], pa2[5], pm); emit(5);
+                    step_records<6>(X, Y, pa[6], pa2[6], pm); emit(6);
+                    step_records<7>(X, Y, pa[7], pa2[7], pm); emit(7);
                     if (SCORES && hvalid) {
-                        const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + pa[kTP]);
-                        const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + pa2[kTP]);
+                        const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + (pa[kTP] - dsm_s));
+                        const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + (pa2[kTP] - dsm_s));
                         halo_store(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
                     }
                 } else {
