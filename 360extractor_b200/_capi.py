@@ -51,6 +51,7 @@ SYMBOLS = {
     "x360_blur_sums": (ctypes.c_int, [_i32, _vp, _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "x360_lanczos4_table": (ctypes.c_int, [_vp]),
     "x360_focal": (_dbl, [_i32, _dbl]),
+    "x360_plan_preview": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(_i32), _vp, _vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "x360_host_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp)]),
     "x360_host_free": (ctypes.c_int, [_vp]),
     "x360_last_error": (ctypes.c_char_p, []),
@@ -67,11 +68,12 @@ def lib() -> ctypes.CDLL:
     """Load lib/libx360.so.  Raises if it has not been built — there is no other backend."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("X360_LIB", LIB_PATH)      # another build of the same library (tuning experiments)
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m 360extractor_b200.build` "
+                f"{path} is missing: build it with `python -m 360extractor_b200.build` "
                 "(or __graft_entry__.build()).  This package has no CPU or PyTorch fallback.")
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)          # AttributeError here = header / library mismatch
             fn.restype = res

@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "x360_capi.cu")]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("X360_NVCC_EXTRA", "").split(), "-o", LIB_PATH, os.path.join(CSRC, "x360_capi.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -235,15 +235,19 @@ HostUnits build_units(const double *R, int V, int W, bool share)
     return h;
 }
 
-// Host estimate of the per-tile source footprints (9 sample points of each 34x34 tile + halo), to
-// size the staging buffers so that `pct` of the tiles fit: rows and (8-aligned) pixels per row.
-void survey_footprints(const Geom &g, const double *R, int V, double pct, int *rows_out, int *npx_out)
+// Host estimate of the per-tile source footprints (9 sample points of each 34x34 tile incl. halo) ->
+// the staging capacity (footprint rows, raw bytes per row) that maximises
+//   (fraction of tiles that fit) x (throughput factor of the CTAs/SM the shared-memory size allows).
+// Seam-wrapping and pole tiles never fit and go direct whatever the capacity.
+void choose_capacity(const Geom &g, const double *R, int V, int *rows_out, int *bw_out)
 {
-    std::vector<int> rows, npx;
+    std::vector<int> rows, bws;
+    size_t total = 0;
     for (int v = 0; v < V; ++v) {
         const double *Rv = R + 9 * v;
         for (int ty = 0; ty < g.tiles_y; ++ty)
             for (int tx = 0; tx < g.tiles_x; ++tx) {
+                ++total;
                 int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
                 for (int j = 0; j < 3; ++j)
                     for (int i = 0; i < 3; ++i) {
@@ -260,15 +264,29 @@ void survey_footprints(const Geom &g, const double *R, int V, double pct, int *r
                     }
                 if (xmax - xmin > g.W / 2) continue;                      // wraps the seam: never staged
                 rows.push_back(ymax - ymin + 3);
-                npx.push_back(xmax - (xmin & ~3) + 2);
+                const int npx = xmax - (xmin & ~3) + 2;
+                bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);        // worst alignment
             }
     }
-    if (rows.empty()) { *rows_out = 16; *npx_out = 48; return; }
-    std::sort(rows.begin(), rows.end());
-    std::sort(npx.begin(), npx.end());
-    const size_t k = std::min(rows.size() - 1, (size_t)(pct * (double)rows.size()));
-    *rows_out = rows[k];
-    *npx_out = npx[k];
+    // measured on cfg2 (B200): 5 CTAs/SM 1.0, 4 CTAs 0.92; fewer CTAs hide less latency
+    static const double occ_factor[9] = {0.0, 0.35, 0.6, 0.8, 0.92, 1.0, 1.04, 1.06, 1.08};
+    double best = -1.0;
+    int best_rows = 40, best_bw = 144;
+    for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
+        for (int r = 24; r <= 96; r += kTBoxRows) {
+            const size_t smem = tiled_smem_bytes(r, bw) + 1024;
+            if (smem > 110 * 1024) continue;
+            int occ = (int)((227 * 1024) / smem);
+            occ = occ > 8 ? 8 : occ;
+            size_t fit = 0;
+            for (size_t i = 0; i < rows.size(); ++i) fit += (rows[i] <= r && bws[i] <= bw);
+            const double cover = total ? (double)fit / (double)total : 0.0;
+            // tiles that do not fit run ~3x slower through the direct gathers
+            const double score = occ_factor[occ] / (cover + 3.0 * (1.0 - cover));
+            if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; }
+        }
+    *rows_out = best_rows;
+    *bw_out = best_bw;
 }
 
 }  // namespace
@@ -395,6 +413,29 @@ int x360_lanczos4_table(int16_t *out)
 
 double x360_focal(int32_t out_w, double fov_deg) { return focal_of(out_w, fov_deg); }
 
+int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,
+                      int32_t *rows_max, int32_t *bw_max)
+{
+    if (!params || !params->R || params->n_views < 1) return fail(X360_E_INVALID, "null argument");
+    if (params->struct_size != (int32_t)sizeof(x360_params)) return fail(X360_E_INVALID, "x360_params.struct_size mismatch");
+    if (int rc = check_dims(params->src_w, params->src_h, params->out_w, params->out_h)) return rc;
+    if (!(params->fov_deg > 0.0 && params->fov_deg < 180.0)) return fail(X360_E_INVALID, "fov_deg %g outside (0, 180)", params->fov_deg);
+    const HostUnits h = build_units(params->R, params->n_views, params->src_w, true);
+    if (n_units) *n_units = (int32_t)h.units.size();
+    for (size_t u = 0; u < h.units.size(); ++u)
+        for (int i = 0; i < h.units[u].n; ++i) {
+            const int e = h.units[u].first + i;
+            if (unit_of_view) unit_of_view[h.view[e]] = (int32_t)u;
+            if (shift_px) shift_px[h.view[e]] = h.shift[e];
+        }
+    int rows = 0, bw = 0;
+    choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
+                    params->n_views, &rows, &bw);
+    if (rows_max) *rows_max = rows;
+    if (bw_max) *bw_max = bw;
+    return X360_OK;
+}
+
 int x360_plan_create(const x360_params *params, x360_plan **out_plan)
 {
     if (!params || !out_plan) return fail(X360_E_INVALID, "null argument");
@@ -429,15 +470,10 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->path = (params->interp == X360_INTERP_LANCZOS4 || params->path == X360_PATH_DIRECT) ? X360_PATH_DIRECT
                : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
     if (pl->path == X360_PATH_TILED) {
-        // staging capacity from a host survey of the tiles' footprints: X360_STAGE_PCT of them fit
-        double pct = 0.97;
-        if (const char *e = getenv("X360_STAGE_PCT")) pct = atof(e) > 0.0 && atof(e) < 1.0 ? atof(e) : pct;
-        int rows = 0, npx = 0;
-        survey_footprints(pl->g, params->R, params->n_views, pct, &rows, &npx);
-        int bw = (12 + 3 * (npx + 1) + 47) / 48 * 48;              // raw bytes per footprint row, worst alignment
-        bw = bw < 96 ? 96 : (bw > 48 * kTNumBoxW ? 48 * kTNumBoxW : bw);
+        // staging capacity from a host survey of the tiles' footprints
+        int rows = 40, bw = 144;
+        choose_capacity(pl->g, params->R, params->n_views, &rows, &bw);
         if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
-        rows = round_up(rows < 24 ? 24 : rows, kTBoxRows);
         if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
         while (rows > 24 && tiled_smem_bytes(rows, bw) > 100 * 1024) rows -= kTBoxRows;
         pl->t_bw = bw;

@@ -41,8 +41,13 @@
 
 namespace x360 {
 
-constexpr int kTT = 128;              // threads per CTA: 4 warps, warp w owns tile rows 8w .. 8w+7
-constexpr int kTP = 8;                // output pixels (rows) per thread
+#ifndef X360_TILED_PX
+#define X360_TILED_PX 8
+#endif
+constexpr int kTP = X360_TILED_PX;    // output pixels (rows) per thread: warp w owns tile rows kTP w .. kTP w + kTP - 1
+constexpr int kTT = kTile * kTile / kTP;   // threads per CTA (128: 4 warps)
+constexpr int kTW = kTT / 32;         // warps per CTA
+static_assert(kTP == 8 || kTP == 4, "the gather is written out for 8 or 4 rows per thread");
 constexpr int kTBoxRows = 8;          // granularity of the footprint row capacity
 constexpr int kTNumBoxW = 5;          // load box widths 48, 96, 144, 192, 240 bytes (16, 32, ... source pixels)
 constexpr int kTNumBoxH = 3;          // load box heights rows_max - 16, rows_max - 8, rows_max
@@ -79,7 +84,7 @@ struct TiledArgs {
 };
 
 struct TiledCtrl {
-    int wbb[4][4];                    // per-warp footprint bounding boxes (16-B aligned rows)
+    int wbb[kTW][4];                  // per-warp footprint bounding boxes (16-B aligned rows)
     unsigned long long mbar;
     long long sums[2];
     int item;
@@ -95,12 +100,12 @@ struct TiledCtrl {
 //        records stay within 144 B for the gather's LDS.64.  Record x of footprint row r lives at
 //        r * 3 bw + (x >> 4) * 144 + (x & 15) * 8.
 constexpr uint32_t kOffCtl = 0;
-constexpr uint32_t kOffTile = 128;
+constexpr uint32_t kOffTile = 256;
 constexpr uint32_t kOffU0 = kOffTile + 2 * kTile * kTile * 3;
 constexpr uint32_t kOffSy = kOffU0 + kTile * kTile * 8;
 constexpr uint32_t kOffGray = kOffSy + kTile * kTile * 4;
 constexpr uint32_t kOffRaw = (kOffGray + (uint32_t)sizeof(GrayTile) + 127u) & ~127u;
-static_assert(sizeof(TiledCtrl) <= 128, "ctrl block");
+static_assert(sizeof(TiledCtrl) <= 256, "ctrl block");
 
 __host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 128u + 127u) & ~127u; }
 __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max)
@@ -193,7 +198,7 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t s
 }
 
 template <bool SCORES>
-__global__ void __launch_bounds__(kTT, SCORES ? 4 : 5)
+__global__ void __launch_bounds__(kTT, kTW == 4 ? (SCORES ? 4 : 5) : (SCORES ? 3 : 4))
 extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
@@ -254,7 +259,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 u0s[k * kTT + tid] = uf;
                 sy_s[k * kTT + tid] = q5_of(my);
             }
-            if (SCORES) {
+            if (SCORES && tid < 128) {
                 int hx, hy;
                 halo_coords(tid, x0, y0, hx, hy);
                 hvalid = (hx >= 0 && hx < g.ow && hy >= 0 && hy < g.oh);
@@ -301,7 +306,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
             if (tid == 0) { ctl.sums[0] = 0; ctl.sums[1] = 0; }
             __syncthreads();
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < kTW; ++w) {
                 const int4 b = *reinterpret_cast<const int4 *>(ctl.wbb[w]);
                 xmin = min(xmin, b.x); xmax = max(xmax, b.y); ymin = min(ymin, b.z); ymax = max(ymax, b.w);
             }
@@ -357,9 +362,10 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
             // vertical reuse: a thread walks down one output column, so consecutive pixels usually share
             // a pair record (same source column; source row the same or one further down).  Two bits
             // per pixel: 0 keep both records, 1 lower record becomes the upper one (load one), 2 load both.
-            uint32_t pm = 3u;
+            uint32_t pm = 3u | (3u << kTP);                 // two independent chains (rows 0..kTP/2-1 and the rest), interleaved for ILP
 #pragma unroll
             for (int k = 1; k < kTP; ++k) {
+                if (k == kTP / 2) continue;
                 const bool same = (sxs[k] >> 5) == (sxs[k - 1] >> 5);
                 const int adv = (sys[k] >> 5) - (sys[k - 1] >> 5);
                 pm |= ((same && adv == 0) ? 0u : ((same && adv == 1) ? 1u : 3u)) << (2 * k);
@@ -403,20 +409,24 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 if (staged) {
                     if (f + 1 < f_end && tid == 32) issue_box(f + 1);
                     uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u);          // upper / lower pair record, carried down the column
-                    auto emit = [&](int k) {
-                        const uint32_t pxl = combine_pairs(X, Y, pb[k], pc[k]);
+                    uint2 X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);        // second chain (rows 4-7)
+                    auto emit = [&](int k, const uint2 &U, const uint2 &V) {
+                        const uint32_t pxl = combine_pairs(U, V, pb[k], pc[k]);
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     };
-                    step_records<0>(X, Y, pa[0], pa2[0], pm); emit(0);
-                    step_records<1>(X, Y, pa[1], pa2[1], pm); emit(1);
-                    step_records<2>(X, Y, pa[2], pa2[2], pm); emit(2);
-                    step_records<3>(X, Y, pa[3], pa2[3], pm); emit(3);
-                    step_records<4>(X, Y, pa[4], pa2[4], pm); emit(4);
-                    step_records<5>(X, Y, pa[5], pa2[5], pm); emit(5);
-                    step_records<6>(X, Y, pa[6], pa2[6], pm); emit(6);
-                    step_records<7>(X, Y, pa[7], pa2[7], pm); emit(7);
+                    constexpr int HC = kTP / 2;
+                    step_records<0>(X, Y, pa[0], pa2[0], pm); step_records<HC>(X2, Y2, pa[HC], pa2[HC], pm);
+                    emit(0, X, Y); emit(HC, X2, Y2);
+                    step_records<1>(X, Y, pa[1], pa2[1], pm); step_records<HC + 1>(X2, Y2, pa[HC + 1], pa2[HC + 1], pm);
+                    emit(1, X, Y); emit(HC + 1, X2, Y2);
+                    if constexpr (kTP == 8) {
+                        step_records<2>(X, Y, pa[2], pa2[2], pm); step_records<6>(X2, Y2, pa[6], pa2[6], pm);
+                        emit(2, X, Y); emit(6, X2, Y2);
+                        step_records<3>(X, Y, pa[3], pa2[3], pm); step_records<7>(X2, Y2, pa[7], pa2[7], pm);
+                        emit(3, X, Y); emit(7, X2, Y2);
+                    }
                     if (SCORES && hvalid) {
                         const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + (pa[kTP] - dsm_s));
                         const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + (pa2[kTP] - dsm_s));
@@ -454,7 +464,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 if (SCORES) {
                     int pl = 0; unsigned pl2 = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < 256 / kTT; ++h) {
                         int l1; unsigned l2;
                         laplacian_partial(gt, g, x0, y0, full, tid + h * kTT, l1, l2);
                         pl += l1; pl2 += l2;

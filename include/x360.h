@@ -132,6 +132,18 @@ int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, i
  */
 int x360_lanczos4_table(int16_t *out_tab);
 double x360_focal(int32_t out_w, double fov_deg);
+/*
+ * How the tiled bilinear path would organise a plan (host-only, no device needed):
+ *   n_units       number of view units; the views of a unit differ only by a yaw (ring layouts, the four
+ *                 horizontal cube faces: src/core/geometry.py:24-37,71-75), so they share ONE map evaluation
+ *   unit_of_view  [n_views] unit index of each view (units are ordered largest first)
+ *   shift_px      [n_views] map_x shift of the view relative to its unit's first view, in source pixels [0, W)
+ *   rows_max, bw_max  staging capacity chosen from a survey of the tiles' source footprints
+ *                 (footprint rows; raw bytes per footprint row, a multiple of 48)
+ * Any output pointer may be NULL.
+ */
+int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,
+                      int32_t *rows_max, int32_t *bw_max);
 
 /* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
 int x360_host_alloc(size_t bytes, void **out_ptr);

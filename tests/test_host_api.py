@@ -196,3 +196,37 @@ def test_blur_filter_from_settings_defaults(x360):
     assert (f.enabled, f.smart, f.threshold) == (False, False, 100.0)   # processor.py:219-221
     f = x360.BlurFilter.from_settings({"blur_filter_enabled": True, "smart_blur_enabled": True, "blur_threshold": 42.5})
     assert (f.enabled, f.smart, f.threshold) == (True, True, 42.5)
+
+
+# ---- plan preview: view units that share a map, staging capacity (host-only logic of the tiled path) ----
+def test_plan_preview_view_units(x360):
+    """Views that differ only by a yaw (ring: geometry.py:71-75; the 4 horizontal cube faces: :30-35)
+    share one map evaluation; their map_x is shifted by yaw / 360 * W."""
+    def preview(layout, n, pitch, H=2880, W=5760, d=1600):
+        views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout)
+        return views, x360.plan_preview(H, W, d, 90, x360.rotation_stack(views)[1])
+
+    views, pv = preview("ring", 8, 0)
+    assert pv["n_units"] == 1 and pv["unit_of_view"] == [0] * 8
+    np.testing.assert_allclose(pv["shift_px"], [v[1] / 360.0 * 5760 for v in views], rtol=0, atol=1e-9)
+    views, pv = preview("ring", 8, -20)                                  # inclination does not break the sharing
+    assert pv["n_units"] == 1
+    np.testing.assert_allclose(pv["shift_px"], [v[1] / 360.0 * 5760 for v in views], rtol=0, atol=1e-9)
+    views, pv = preview("cube", 6, 0)                                    # Front/Right/Back/Left share, Up and Down do not
+    assert pv["n_units"] == 3 and pv["unit_of_view"] == [0, 0, 0, 0, 1, 2]
+    np.testing.assert_allclose(pv["shift_px"][:4], [0, 1440, 2880, 4320], rtol=0, atol=1e-9)
+    views, pv = preview("fibonacci", 7, -20)                             # every view has its own pitch
+    assert pv["n_units"] == 7 and pv["shift_px"] == [0.0] * 7
+    views, pv = preview("ring", 36, 0)                                   # at most 8 views per unit
+    assert pv["n_units"] == 5 and pv["unit_of_view"].count(0) == 8 and pv["unit_of_view"].count(4) == 4
+    assert all(0.0 <= s < 5760 for s in pv["shift_px"])
+
+
+def test_plan_preview_capacity(x360):
+    views = x360.GeometryProcessor.generate_views(8, 0, "ring")
+    pv = x360.plan_preview(2880, 5760, 1600, 90, x360.rotation_stack(views)[1])
+    # 32 output rows cover at most 32 * (W / 2 pi) / f = 36.7 source rows (+ the lower tap, + slack)
+    assert 38 <= pv["rows_max"] <= 48 and pv["rows_max"] % 8 == 0
+    assert pv["bw_max"] in (96, 144, 192, 240)
+    with pytest.raises(x360.X360Error):
+        x360.plan_preview(2880, 5760, 1600, 190, x360.rotation_stack(views)[1])
