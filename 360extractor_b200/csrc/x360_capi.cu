@@ -274,7 +274,7 @@ void choose_capacity(const Geom &g, const double *R, int V, int *rows_out, int *
     int best_rows = 40, best_bw = 144;
     for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
         for (int r = 24; r <= 96; r += kTBoxRows) {
-            const size_t smem = tiled_smem_bytes(r, bw) + 1024;
+            const size_t smem = tiled_smem_bytes(r, bw, false) + 1024;
             if (smem > 110 * 1024) continue;
             int occ = (int)((227 * 1024) / smem);
             occ = occ > 8 ? 8 : occ;
@@ -303,7 +303,7 @@ struct x360_plan {
     unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
     // tiled path
     int t_bw = 144, t_rows = 40, n_units = 0;
-    size_t t_smem = 0;
+    size_t t_smem[2] = {0, 0};           // dynamic shared memory without / with scores
     TiledUnit *d_units = nullptr;
     int *d_unit_view = nullptr;
     double *d_unit_shift = nullptr;
@@ -321,7 +321,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores), kTT, pl->t_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores), kTT, pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -391,7 +391,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores)<<<grid, kTT, pl->t_smem, st>>>(a, tms);
+    pick_tiled(scores)<<<grid, kTT, pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -475,15 +475,16 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         choose_capacity(pl->g, params->R, params->n_views, &rows, &bw);
         if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
         if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-        while (rows > 24 && tiled_smem_bytes(rows, bw) > 100 * 1024) rows -= kTBoxRows;
+        while (rows > 24 && tiled_smem_bytes(rows, bw, true) > 100 * 1024) rows -= kTBoxRows;
         pl->t_bw = bw;
         pl->t_rows = rows;
-        pl->t_smem = tiled_smem_bytes(rows, bw);
         for (int sc = 0; sc < 2; ++sc) {
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem);
+            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
+                const size_t want = pl->t_smem[sc];
                 delete pl;
-                return fail(X360_E_CUDA, "cannot reserve %zu B of shared memory: %s", pl->t_smem, cudaGetErrorString(ea));
+                return fail(X360_E_CUDA, "cannot reserve %zu B of shared memory: %s", want, cudaGetErrorString(ea));
             }
         }
     }
@@ -567,7 +568,7 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (path) *path = pl->path;
     if (grid) *grid = plan_grid(pl, false);
     if (block) *block = pl->path == X360_PATH_TILED ? kTT : kThreads;
-    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->t_smem
+    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->t_smem[0]
                                   : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
     return X360_OK;
 }

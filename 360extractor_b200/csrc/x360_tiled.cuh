@@ -85,7 +85,7 @@ struct TiledArgs {
 
 struct TiledCtrl {
     int wbb[kTW][4];                  // per-warp footprint bounding boxes (16-B aligned rows)
-    unsigned long long mbar;
+    unsigned long long mbar[2];       // one per raw buffer
     long long sums[2];
     int item;
 };
@@ -100,17 +100,19 @@ struct TiledCtrl {
 //        records stay within 144 B for the gather's LDS.64.  Record x of footprint row r lives at
 //        r * 3 bw + (x >> 4) * 144 + (x & 15) * 8.
 constexpr uint32_t kOffCtl = 0;
-constexpr uint32_t kOffTile = 256;
-constexpr uint32_t kOffU0 = kOffTile + 2 * kTile * kTile * 3;
+constexpr uint32_t kOffTile = 128;
+constexpr uint32_t kOffU0 = kOffTile + kTile * kTile * 3;
 constexpr uint32_t kOffSy = kOffU0 + kTile * kTile * 8;
 constexpr uint32_t kOffGray = kOffSy + kTile * kTile * 4;
-constexpr uint32_t kOffRaw = (kOffGray + (uint32_t)sizeof(GrayTile) + 127u) & ~127u;
-static_assert(sizeof(TiledCtrl) <= 256, "ctrl block");
+__host__ __device__ constexpr uint32_t tiled_off_raw(bool scores) { return scores ? ((kOffGray + (uint32_t)sizeof(GrayTile) + 127u) & ~127u) : kOffGray; }
+static_assert(sizeof(TiledCtrl) <= 128, "ctrl block");
+static_assert(kOffGray % 128 == 0, "raw buffers must be 128-byte aligned");
 
-__host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 128u + 127u) & ~127u; }
-__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max)
+// one raw buffer: rows_max x bw_max, rounded up to the TMA destination alignment
+__host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 127u) & ~127u; }
+__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores)
 {
-    return (size_t)kOffRaw + tiled_raw_bytes(rows_max, bw_max) + (size_t)rows_max * 3 * bw_max + 256;
+    return (size_t)tiled_off_raw(scores) + 2 * tiled_raw_bytes(rows_max, bw_max) + (size_t)rows_max * 3 * bw_max + 16;
 }
 
 // geometry.py:149-186 for one output pixel: fp64 map_x (unrounded) and float32 map_y.
@@ -214,13 +216,15 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
     double *const u0s = reinterpret_cast<double *>(dsm + kOffU0);
     int *const sy_s = reinterpret_cast<int *>(dsm + kOffSy);
     GrayTile &gt = *reinterpret_cast<GrayTile *>(dsm + kOffGray);
-    const uint32_t off_pairs = kOffRaw + tiled_raw_bytes(a.rows_max, a.bw_max);     // dsm-relative
+    constexpr uint32_t kOffRaw = tiled_off_raw(SCORES);
+    const uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
+    const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
 
-    if (tid == 0) mbar_init(&ctl.mbar, 1);
-    uint32_t phase = 0;
-    uint32_t it = 0;                  // frames processed by this CTA: selects the packed-tile buffer
+    if (tid == 0) { mbar_init(&ctl.mbar[0], 1); mbar_init(&ctl.mbar[1], 1); }
+    uint32_t phase = 0;               // bit b: parity of raw buffer b's mbarrier
+    uint32_t it = 0;                  // frames processed by this CTA: selects the raw buffer
 
     // frame-invariant: where this lane's packed word of row k goes (+ k * 96), and how it is built
     const int q = lane & 3;
@@ -373,41 +377,44 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
 
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
             const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
-            uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;
+            uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;                 // in raw buffer 0
             uint32_t tdst0 = off_pairs + 32u * tid + 16u * (tid >> 2);
             asm volatile("" : "+r"(tsrc0), "+r"(tdst0));                 // hoisted out of the frame loop for good
             const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
-            auto issue_box = [&](int f) {                                // one thread
-                mbar_arrive_expect_tx(&ctl.mbar, box_rows * bw);
-                tma_load_box(raw_s, tm, gx0, y_org, f, &ctl.mbar);
+            auto issue_box = [&](int f, uint32_t b) {                    // one thread: frame f -> raw buffer b
+                mbar_arrive_expect_tx(&ctl.mbar[b], box_rows * bw);
+                tma_load_box(raw_s + b * raw_bytes, tm, gx0, y_org, f, &ctl.mbar[b]);
             };
-            if (staged && tid == 0) issue_box(f_begin);
+            if (staged && tid == 0) {                                    // two frames in flight
+                issue_box(f_begin, it & 1u);
+                if (f_begin + 1 < f_end) issue_box(f_begin + 1, (it + 1u) & 1u);
+            }
 
             // ---- 4. walk the frame chunk ---------------------------------------------------------
             const uint8_t *fb = a.frames + (size_t)f_begin * frame_bytes;
             for (int f = f_begin; f < f_end; ++f, fb += frame_bytes, ++it) {
-                const uint32_t ob = (it & 1u) * (kTile * kTile * 3);
+                const uint32_t rb = it & 1u;
                 if (staged) {
-                    mbar_wait(&ctl.mbar, phase);
-                    phase ^= 1u;
-                    uint32_t src = tsrc0, dst = tdst0;
+                    mbar_wait(&ctl.mbar[rb], (phase >> rb) & 1u);
+                    phase ^= 1u << rb;
+                    uint32_t src = tsrc0 + rb * raw_bytes, dst = tdst0;
 #pragma unroll 2
                     for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 36u * kTT)
                         transform_group(dsm + src, dsm + dst);
                 }
-                // the TMA store that last read this frame's tile buffer (two frames ago) must be done
-                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                // the TMA store of the previous frame must have finished reading the packed tile
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncthreads();                      // pairs ready, raw consumed, tile buffer free
                 if (SCORES && tid == 0 && f > f_begin) {
                     atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f - 1) * a.V + v], (unsigned long long)ctl.sums[0]);
                     atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f - 1) * a.V + v], (unsigned long long)ctl.sums[1]);
                     ctl.sums[0] = 0; ctl.sums[1] = 0;
                 }
-                uint32_t obase = kOffTile + ob + my_word;
+                uint32_t obase = kOffTile + my_word;
                 asm volatile("" : "+r"(obase));
                 uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
                 if (staged) {
-                    if (f + 1 < f_end && tid == 32) issue_box(f + 1);
+                    if (f + 2 < f_end && tid == 32) issue_box(f + 2, rb);          // this frame's raw rows are consumed
                     uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u);          // upper / lower pair record, carried down the column
                     uint2 X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);        // second chain (rows 4-7)
                     auto emit = [&](int k, const uint2 &U, const uint2 &V) {
@@ -452,13 +459,13 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 __syncthreads();                      // tile (+ gray halo) complete; pairs free for the next frame
 
                 if (a.store_ok) {
-                    if (tid == 0) tma_store_tile(&tms.out, otile_s + ob, x0 * 3, y0, f * a.V + v);
+                    if (tid == 0) tma_store_tile(&tms.out, otile_s, x0 * 3, y0, f * a.V + v);
                 } else {
                     const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(kTile, g.oh - y0);
                     uint8_t *out_view = a.out + ((size_t)f * a.V + v) * view_bytes;
                     for (int i = tid; i < kTile * kTile * 3; i += kTT) {
                         const int row = i / (kTile * 3), bb = i - row * (kTile * 3);
-                        if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = otile[ob + i];
+                        if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = otile[i];
                     }
                 }
                 if (SCORES) {
