@@ -168,6 +168,20 @@ template <int K> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y
                  : "r"(a_upper), "r"(a_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
 }
 
+// The same walking UP the column (pixel K after pixel K+1): bit 2K = the upper record becomes the
+// lower one and a new upper record is loaded; bit 2K+1 = the lower record is loaded too.
+template <int K> __device__ __forceinline__ void step_records_up(uint2 &X, uint2 &Y, uint32_t a_upper, uint32_t a_lower, uint32_t pm)
+{
+    asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %6, %7;\n\tsetp.ne.u32 pA, t, 0;\n\t"
+                 "and.b32 t, %6, %8;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                 "@pB mov.b32 %2, %0;\n\t@pB mov.b32 %3, %1;\n\t"
+                 "@pB ld.shared.v2.u32 {%0, %1}, [%4];\n\t"
+                 "@pA ld.shared.v2.u32 {%2, %3}, [%5];\n\t}"
+                 : "+r"(X.x), "+r"(X.y), "+r"(Y.x), "+r"(Y.y)
+                 : "r"(a_upper), "r"(a_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
+}
+
 // pair-record words of source pixel J of a 4-pixel group from its packed BGR words w[0..3]
 template <int J> __device__ __forceinline__ uint32_t pair_lo(const uint32_t (&w)[4])
 {
@@ -366,12 +380,16 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
             // vertical reuse: a thread walks down one output column, so consecutive pixels usually share
             // a pair record (same source column; source row the same or one further down).  Two bits
             // per pixel: 0 keep both records, 1 lower record becomes the upper one (load one), 2 load both.
-            uint32_t pm = 3u | (3u << kTP);                 // two independent chains (rows 0..kTP/2-1 and the rest), interleaved for ILP
+            // Two chains start from the middle rows and walk apart (interleaved for ILP): rows HC-1 .. 0 upwards
+            // (modes relative to the pixel below) and rows HC .. kTP-1 downwards (relative to the pixel above).
+            constexpr int HC = kTP / 2;
+            uint32_t pm = 3u << (2 * (HC - 1));
 #pragma unroll
-            for (int k = 1; k < kTP; ++k) {
-                if (k == kTP / 2) continue;
-                const bool same = (sxs[k] >> 5) == (sxs[k - 1] >> 5);
-                const int adv = (sys[k] >> 5) - (sys[k - 1] >> 5);
+            for (int k = 0; k < kTP; ++k) {
+                if (k == HC - 1) continue;
+                const int o = k < HC ? k + 1 : k - 1;                 // the pixel this one is derived from
+                const bool same = (sxs[k] >> 5) == (sxs[o] >> 5);
+                const int adv = k < HC ? (sys[o] >> 5) - (sys[k] >> 5) : (sys[k] >> 5) - (sys[o] >> 5);
                 pm |= ((same && adv == 0) ? 0u : ((same && adv == 1) ? 1u : 3u)) << (2 * k);
             }
 
@@ -423,16 +441,17 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     };
-                    constexpr int HC = kTP / 2;
-                    step_records<0>(X, Y, pa[0], pa2[0], pm); step_records<HC>(X2, Y2, pa[HC], pa2[HC], pm);
-                    emit(0, X, Y); emit(HC, X2, Y2);
-                    step_records<1>(X, Y, pa[1], pa2[1], pm); step_records<HC + 1>(X2, Y2, pa[HC + 1], pa2[HC + 1], pm);
-                    emit(1, X, Y); emit(HC + 1, X2, Y2);
+                    step_records<HC - 1>(X, Y, pa[HC - 1], pa2[HC - 1], pm);          // both records (mode 3)
+                    X2 = X; Y2 = Y;
+                    step_records<HC>(X2, Y2, pa[HC], pa2[HC], pm);
+                    emit(HC - 1, X, Y); emit(HC, X2, Y2);
+                    step_records_up<HC - 2>(X, Y, pa[HC - 2], pa2[HC - 2], pm); step_records<HC + 1>(X2, Y2, pa[HC + 1], pa2[HC + 1], pm);
+                    emit(HC - 2, X, Y); emit(HC + 1, X2, Y2);
                     if constexpr (kTP == 8) {
-                        step_records<2>(X, Y, pa[2], pa2[2], pm); step_records<6>(X2, Y2, pa[6], pa2[6], pm);
-                        emit(2, X, Y); emit(6, X2, Y2);
-                        step_records<3>(X, Y, pa[3], pa2[3], pm); step_records<7>(X2, Y2, pa[7], pa2[7], pm);
-                        emit(3, X, Y); emit(7, X2, Y2);
+                        step_records_up<1>(X, Y, pa[1], pa2[1], pm); step_records<6>(X2, Y2, pa[6], pa2[6], pm);
+                        emit(1, X, Y); emit(6, X2, Y2);
+                        step_records_up<0>(X, Y, pa[0], pa2[0], pm); step_records<7>(X2, Y2, pa[7], pa2[7], pm);
+                        emit(0, X, Y); emit(7, X2, Y2);
                     }
                     if (SCORES && hvalid) {
                         const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + (pa[kTP] - dsm_s));
