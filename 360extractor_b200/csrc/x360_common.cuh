@@ -58,12 +58,48 @@ __device__ __forceinline__ int wrap_idx(int p, int len)
 
 __device__ __forceinline__ int sat_s16(int v) { return max(-32768, min(32767, v)); }
 
-// geometry.py:149-190 for one output pixel -> the float32 (map_x, map_y) pair.
-// All roundings are explicit (no contraction) so the only freedom left against numpy
-// is the last-ulp behaviour of atan2/asin, which the float32 cast + Q5 rounding absorbs
-// except with probability ~1e-10 per pixel ("map exactness").
-__device__ __forceinline__ void map_f32(const double *__restrict__ R, const Geom &g, int x, int y,
-                                        float &mx, float &my)
+// ---- fp64 atan2 for the map ------------------------------------------------------------------
+// The map needs atan2 / asin to within a few ulp ("map exactness"); CUDA's libm
+// versions cost ~200 instructions each.  This one: one division (argument reduced to
+// |z| <= tan(pi/8) by folding (mn - mx)/(mn + mx) into the same quotient), an odd polynomial
+// z + z w Q(w), w = z^2 (coefficients from scripts/atan_coeffs.py: Chebyshev fit at 50 digits, max
+// relative error 6.5e-17 in double evaluation), quadrant assembly with hi + lo constants.
+__device__ __forceinline__ double fast_atan2(double y, double x)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool red = mn > 0x1.a827999fcef32p-2 * mx;                 // tan(pi/8)
+    const double num = red ? mn - mx : mn;
+    const double den = red ? mn + mx : mx;
+    double z = __ddiv_rn(num, den);
+    if (mx == 0.0) z = 0.0;                                          // atan2(+-0, +-0)
+    const double w = z * z;
+    double q = -0x1.a71378d0839b7p-7;
+    q = fma(q, w, 0x1.e3ded60e0b4b5p-6);
+    q = fma(q, w, -0x1.4bdeae2516d21p-5);
+    q = fma(q, w, 0x1.816326bd079a1p-5);
+    q = fma(q, w, -0x1.ae847c59c5c84p-5);
+    q = fma(q, w, 0x1.e1d20955386eap-5);
+    q = fma(q, w, -0x1.111085dfdddd8p-4);
+    q = fma(q, w, 0x1.3b13aa8a180dbp-4);
+    q = fma(q, w, -0x1.745d170db805ep-4);
+    q = fma(q, w, 0x1.c71c71c5eae8cp-4);
+    q = fma(q, w, -0x1.249249249055bp-3);
+    q = fma(q, w, 0x1.9999999999964p-3);
+    q = fma(q, w, -0x1.5555555555555p-2);
+    double a = fma(z, q * w, z);                                     // atan(z), |z| <= tan(pi/8)
+    if (red) a = 0x1.921fb54442d18p-1 + (a + 0x1.1a62633145c07p-55); // pi/4 + atan(z)
+    if (ay > ax) a = 0x1.921fb54442d18p+0 - (a - 0x1.1a62633145c07p-54);   // pi/2 - a
+    if (signbit(x)) a = 0x1.921fb54442d18p+1 - (a - 0x1.1a62633145c07p-53); // pi - a
+    return copysign(a, y);
+}
+
+// geometry.py:149-190 for one output pixel -> fp64 map_x (unrounded) and the float32 map_y.
+// Every rounding of the reference's sequence is kept (no contraction); the only freedom against
+// numpy is the last ulps of atan2 / asin (asin(v1 / |v|) is evaluated as atan2(v1, hypot(v0, v2))),
+// which the float32 cast + Q5 rounding absorbs except with probability ~1e-10 per pixel
+// ("map exactness").
+__device__ __forceinline__ void map_f64(const double *__restrict__ R, const Geom &g, int x, int y, double &uf, float &my)
 {
     const double xn = __ddiv_rn((double)x - g.cx, g.f);
     const double yn = __ddiv_rn((double)y - g.cy, g.f);
@@ -71,13 +107,18 @@ __device__ __forceinline__ void map_f32(const double *__restrict__ R, const Geom
     const double v0 = __dadd_rn(__fma_rn(yn, R[1], __dmul_rn(xn, R[0])), R[2]);
     const double v1 = __dadd_rn(__fma_rn(yn, R[4], __dmul_rn(xn, R[3])), R[5]);
     const double v2 = __dadd_rn(__fma_rn(yn, R[7], __dmul_rn(xn, R[6])), R[8]);
-    const double theta = atan2(v0, v2);
-    const double rr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)), __dmul_rn(v2, v2)));
-    const double phi = asin(__ddiv_rn(v1, rr));
-    const double uf = __dmul_rn(__dadd_rn(__ddiv_rn(theta, kTwoPi), 0.5), (double)g.W);
-    const double vf = __dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H);
+    const double theta = fast_atan2(v0, v2);
+    const double phi = fast_atan2(v1, sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v2, v2))));
+    uf = __dmul_rn(__dadd_rn(__ddiv_rn(theta, kTwoPi), 0.5), (double)g.W);
+    my = __double2float_rn(__dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H));
+}
+
+__device__ __forceinline__ void map_f32(const double *__restrict__ R, const Geom &g, int x, int y,
+                                        float &mx, float &my)
+{
+    double uf;
+    map_f64(R, g, x, y, uf, my);
     mx = __double2float_rn(uf);
-    my = __double2float_rn(vf);
 }
 
 // float32 map value -> Q5 exactly like cv2.remap: cvRound(m * 32), round-half-even

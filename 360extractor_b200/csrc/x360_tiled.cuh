@@ -115,21 +115,6 @@ __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, boo
     return (size_t)tiled_off_raw(scores) + 2 * tiled_raw_bytes(rows_max, bw_max) + (size_t)rows_max * 3 * bw_max + 16;
 }
 
-// geometry.py:149-186 for one output pixel: fp64 map_x (unrounded) and float32 map_y.
-__device__ __forceinline__ void map_base(const double *__restrict__ R, const Geom &g, int x, int y, double &uf, float &my)
-{
-    const double xn = __ddiv_rn((double)x - g.cx, g.f);
-    const double yn = __ddiv_rn((double)y - g.cy, g.f);
-    const double v0 = __dadd_rn(__fma_rn(yn, R[1], __dmul_rn(xn, R[0])), R[2]);
-    const double v1 = __dadd_rn(__fma_rn(yn, R[4], __dmul_rn(xn, R[3])), R[5]);
-    const double v2 = __dadd_rn(__fma_rn(yn, R[7], __dmul_rn(xn, R[6])), R[8]);
-    const double theta = atan2(v0, v2);
-    const double rr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)), __dmul_rn(v2, v2)));
-    const double phi = asin(__ddiv_rn(v1, rr));
-    uf = __dmul_rn(__dadd_rn(__ddiv_rn(theta, kTwoPi), 0.5), (double)g.W);
-    my = __double2float_rn(__dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H));
-}
-
 __device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a16x2, uint32_t b, uint32_t c)
 {
     uint32_t d;
@@ -273,7 +258,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
 #pragma unroll 1
             for (int k = 0; k < kTP; ++k) {
                 double uf; float my;
-                map_base(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), uf, my);
+                map_f64(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), uf, my);
                 u0s[k * kTT + tid] = uf;
                 sy_s[k * kTT + tid] = q5_of(my);
             }
@@ -283,7 +268,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 hvalid = (hx >= 0 && hx < g.ow && hy >= 0 && hy < g.oh);
                 if (hvalid) {
                     float my;
-                    map_base(R, g, hx, hy, hu0, my);
+                    map_f64(R, g, hx, hy, hu0, my);
                     hsy = q5_of(my);
                 }
             }
