@@ -83,10 +83,13 @@ typedef void (*extract_fn)(const ExtractArgs);
 typedef void (*staged_fn)(const ExtractArgs, const TmapSet);
 
 // The direct extraction kernel for (interpolation, scores); Lanczos4 has the direct path only.
+#ifndef X360_LZ_MINB
+#define X360_LZ_MINB 2
+#endif
 extract_fn pick_direct(int interp, bool scores)
 {
     if (interp == X360_INTERP_LANCZOS4)
-        return scores ? extract_direct<LanczosSampler, true, 2> : extract_direct<LanczosSampler, false, 2>;
+        return scores ? extract_direct<LanczosSampler, true, X360_LZ_MINB> : extract_direct<LanczosSampler, false, X360_LZ_MINB>;
     return scores ? extract_direct<LinearSampler, true, 3> : extract_direct<LinearSampler, false, 4>;
 }
 

@@ -66,6 +66,17 @@ def synth_frames(F, H, W, distribution="smooth"):
     return [np.roll(bases[i % len(bases)], 37 * i, axis=1) for i in range(F)]
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the bench kernel from the committed ncu capture (profiles/traffic.json,
+    written by scripts/ncu_summary.py); None when this workload / batch / kernel has no capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p)).get(key)
+        if t:
+            return t["dram_read_gb"] + t["dram_write_gb"], "profiles/" + t["source"]
+    return None, None
+
+
 def touched_source_pixels(pkg, ex, wl):
     """U of SURVEY.md 8(d): |union over views of source pixels addressed by any tap| for one frame,
     from the plan's own (GPU-made) float32 maps, quantised like cv2.remap does."""
@@ -311,12 +322,15 @@ def main():
     b_alg_frame = 3 * V * d * d + 3 * U + (16 * V if wl["scores"] else 0)
     kernel_ms = statistics.mean(step_ms)            # one extraction kernel per step (+2 tiny memsets with scores)
     achieved = F * b_alg_frame / (kernel_ms * 1e-3) / 1e9
+    kernel_name = ("extract_direct<LanczosSampler,%s>" if wl["mode"] == "lanczos" else
+                   {3: "extract_linear_tiled<%s>", 2: "extract_linear_staged<%s>"}.get(ex.info()["path"], "extract_direct<LinearSampler,%s>")) \
+        % ("scores" if wl["scores"] else "noscores")
+    traffic, traffic_src = measured_traffic(f"{args.workload}:F{F}:{kernel_name}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg_frame,
+                "traffic": traffic, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                "traffic_source": traffic_src, "algorithmic_gb_per_launch": F * b_alg_frame / 1e9, "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg_frame,
                 "touched_source_pixels_per_frame": U, "bytes_per_output_pixel": b_alg_frame / (V * d * d),
-                "kernel": ("extract_direct<LanczosSampler,%s>" if wl["mode"] == "lanczos" else
-                           {3: "extract_linear_tiled<%s>", 2: "extract_linear_staged<%s>"}.get(ex.info()["path"], "extract_direct<LinearSampler,%s>"))
-                          % ("scores" if wl["scores"] else "noscores"),
+                "kernel": kernel_name,
                 "tile_modes": modes,
                 "kernel_ms_mean": kernel_ms, "kernel_ms_min": min(step_ms), "frac_of_nominal_8TBs": achieved / 8000.0}
 
