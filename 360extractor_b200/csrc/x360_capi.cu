@@ -143,7 +143,11 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // ---- tiled path (x360_tiled.cuh) ---------------------------------------------------------------
 typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 
-tiled_fn pick_tiled(bool scores) { return scores ? extract_linear_tiled<true> : extract_linear_tiled<false>; }
+tiled_fn pick_tiled(bool scores, bool lanczos)
+{
+    if (lanczos) return scores ? extract_tiled<true, true> : extract_tiled<false, true>;
+    return scores ? extract_tiled<true, false> : extract_tiled<false, false>;
+}
 
 // load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W];
 // store box {96, 32, 1} of uint8 [F*V][oh][3 ow]
@@ -242,7 +246,7 @@ HostUnits build_units(const double *R, int V, int W, bool share)
 // the staging capacity (footprint rows, raw bytes per row) that maximises
 //   (fraction of tiles that fit) x (throughput factor of the CTAs/SM the shared-memory size allows).
 // Seam-wrapping and pole tiles never fit and go direct whatever the capacity.
-void choose_capacity(const Geom &g, const double *R, int V, int *rows_out, int *bw_out)
+void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, int *rows_out, int *bw_out)
 {
     std::vector<int> rows, bws;
     size_t total = 0;
@@ -266,8 +270,9 @@ void choose_capacity(const Geom &g, const double *R, int V, int *rows_out, int *
                         ymin = std::min(ymin, iy); ymax = std::max(ymax, iy);
                     }
                 if (xmax - xmin > g.W / 2) continue;                      // wraps the seam: never staged
-                rows.push_back(ymax - ymin + 3);
-                const int npx = xmax - (xmin & ~3) + 2;
+                const int m = lanczos ? 7 : 0;                            // 8x8 taps: 3 before, 4 after
+                rows.push_back(ymax - ymin + 3 + m);
+                const int npx = xmax - (xmin & ~3) + 2 + m;
                 bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);        // worst alignment
             }
     }
@@ -277,7 +282,7 @@ void choose_capacity(const Geom &g, const double *R, int V, int *rows_out, int *
     int best_rows = 40, best_bw = 144;
     for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
         for (int r = 24; r <= 96; r += kTBoxRows) {
-            const size_t smem = tiled_smem_bytes(r, bw, false) + 1024;
+            const size_t smem = tiled_smem_bytes(r, bw, false, lanczos) + 1024;
             if (smem > 110 * 1024) continue;
             int occ = (int)((227 * 1024) / smem);
             occ = occ > 8 ? 8 : occ;
@@ -324,7 +329,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores), kTT, pl->t_smem[scores ? 1 : 0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4), kTT, pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -350,6 +355,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.sum_lap = (long long *)sum_lap;
     a.sum_lap2 = (long long *)sum_lap2;
     a.R = pl->d_R;
+    a.lz_tab = pl->d_lz;
     a.units = pl->d_units;
     a.unit_view = pl->d_unit_view;
     a.unit_shift = pl->d_unit_shift;
@@ -394,7 +400,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores)<<<grid, kTT, pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
+    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4)<<<grid, kTT, pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -433,7 +439,7 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
         }
     int rows = 0, bw = 0;
     choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
-                    params->n_views, &rows, &bw);
+                    params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw);
     if (rows_max) *rows_max = rows;
     if (bw_max) *bw_max = bw;
     return X360_OK;
@@ -451,8 +457,8 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (params->interp != X360_INTERP_LINEAR && params->interp != X360_INTERP_LANCZOS4)
         return fail(X360_E_INVALID, "unknown interp %d", params->interp);
     if (params->path < X360_PATH_AUTO || params->path > X360_PATH_TILED) return fail(X360_E_INVALID, "unknown path %d", params->path);
-    if ((params->path == X360_PATH_STAGED || params->path == X360_PATH_TILED) && params->interp == X360_INTERP_LANCZOS4)
-        return fail(X360_E_UNSUPPORTED, "the staged and tiled paths are built for bilinear only; Lanczos4 uses the direct path");
+    if (params->path == X360_PATH_STAGED && params->interp == X360_INTERP_LANCZOS4)
+        return fail(X360_E_UNSUPPORTED, "the staged path is built for bilinear only; Lanczos4 uses the tiled or the direct path");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
         return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
@@ -470,20 +476,20 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->g = make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg);
     pl->sm_count = prop.multiProcessorCount;
     pl->chunk = params->max_batch > 0 ? params->max_batch : 8;
-    pl->path = (params->interp == X360_INTERP_LANCZOS4 || params->path == X360_PATH_DIRECT) ? X360_PATH_DIRECT
+    pl->path = params->path == X360_PATH_DIRECT ? X360_PATH_DIRECT
                : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
     if (pl->path == X360_PATH_TILED) {
         // staging capacity from a host survey of the tiles' footprints
         int rows = 40, bw = 144;
-        choose_capacity(pl->g, params->R, params->n_views, &rows, &bw);
+        choose_capacity(pl->g, params->R, params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw);
         if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
         if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-        while (rows > 24 && tiled_smem_bytes(rows, bw, true) > 100 * 1024) rows -= kTBoxRows;
+        while (rows > 24 && tiled_smem_bytes(rows, bw, true, params->interp == X360_INTERP_LANCZOS4) > 100 * 1024) rows -= kTBoxRows;
         pl->t_bw = bw;
         pl->t_rows = rows;
         for (int sc = 0; sc < 2; ++sc) {
-            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, params->interp == X360_INTERP_LANCZOS4);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, params->interp == X360_INTERP_LANCZOS4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];
                 delete pl;

@@ -36,6 +36,7 @@
 #include <cuda.h>
 
 #include "x360_common.cuh"
+#include "x360_lanczos.cuh"
 #include "x360_linear.cuh"
 #include "x360_staged.cuh"      // mbarrier / TMA load helpers
 
@@ -70,6 +71,7 @@ struct TiledArgs {
     uint8_t *out;                     // [F][V][oh][ow][3]
     long long *sum_lap, *sum_lap2;    // [F][V] or nullptr
     const double *R;                  // [V][9]
+    const int16_t *lz_tab;            // [1024][8][8] Lanczos4 weights (Lanczos4 plans only)
     const TiledUnit *units;           // [n_units], largest units first
     const int *unit_view;             // view index per table entry
     const double *unit_shift;         // map_x shift (source pixels, in [0, W)) per table entry
@@ -110,9 +112,12 @@ static_assert(kOffGray % 128 == 0, "raw buffers must be 128-byte aligned");
 
 // one raw buffer: rows_max x bw_max, rounded up to the TMA destination alignment
 __host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 127u) & ~127u; }
-__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores)
+__host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * 3 * bw_max) + 16u + 15u) & ~15u; }
+__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos)
 {
-    return (size_t)tiled_off_raw(scores) + 2 * tiled_raw_bytes(rows_max, bw_max) + (size_t)rows_max * 3 * bw_max + 16;
+    // ... | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
+    return (size_t)tiled_off_raw(scores) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max) +
+           (lanczos ? (size_t)(kTile * kTile / X360_TILED_PX / 32) * 32 * 144 : 0);
 }
 
 __device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a16x2, uint32_t b, uint32_t c)
@@ -191,6 +196,50 @@ __device__ __forceinline__ void transform_group(const uint8_t *src, uint8_t *dst
     *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(pair_lo<2>(w), pair_hi<2>(w), pair_lo<3>(w), pair_hi<3>(w));
 }
 
+// Lanczos4 from pair records: 8 source rows x 4 records (taps c = 2j, 2j+1) x 3 channels = 96 dp2a with
+// the int16 weight pairs of cv2's table row (w0|w1<<16, ..., w6|w7<<16); contiguous record layout (8 B per
+// source pixel).  dst = sat_u8((sum + 2^14) >> 15) exactly as LanczosSampler::finish.
+//
+// Every pixel has its own (fy, fx) row of the weight table (128 B).  Read directly, each of the 8 loads of
+// a warp touches 32 different cache lines; COOP transposes through shared memory instead: 8 coalesced
+// loads fetch the warp's 32 rows (4 whole lines each), 8 STS.128 park them in this warp's staging area
+// (slot pitch 144 B: conflict-free both ways), and every lane reads its own row back with LDS.128.
+constexpr uint32_t kLzSlot = 144;                        // bytes per staged weight row (128 + 16 pad)
+constexpr uint32_t kLzStage = 32 * kLzSlot;              // per warp
+
+template <bool COOP>
+__device__ __forceinline__ uint32_t lanczos_pairs(uint8_t *dsm, uint32_t a0, uint32_t ppitch, const int16_t *__restrict__ tab,
+                                                  uint32_t tab_off, uint32_t wst, int lane)
+{
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(tab);
+    if (COOP) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t off = __shfl_sync(0xffffffffu, tab_off, 4 * j + (lane >> 3));
+            v[j] = __ldg(reinterpret_cast<const uint4 *>(tb + off) + (lane & 7));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4 *>(dsm + wst + (uint32_t)(4 * j + (lane >> 3)) * kLzSlot + 16u * (lane & 7)) = v[j];
+        __syncwarp();
+    }
+    const uint4 *wrow = COOP ? reinterpret_cast<const uint4 *>(dsm + wst + (uint32_t)lane * kLzSlot)
+                             : reinterpret_cast<const uint4 *>(tb + tab_off);
+    int ab = 0, ag = 0, ar = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r, a0 += ppitch) {
+        const uint4 w = COOP ? wrow[r] : __ldg(wrow + r);
+        const uint2 c0 = *reinterpret_cast<const uint2 *>(dsm + a0), c1 = *reinterpret_cast<const uint2 *>(dsm + a0 + 16);
+        const uint2 c2 = *reinterpret_cast<const uint2 *>(dsm + a0 + 32), c3 = *reinterpret_cast<const uint2 *>(dsm + a0 + 48);
+        ab = dp2a_lo_su(w.w, c3.x, dp2a_lo_su(w.z, c2.x, dp2a_lo_su(w.y, c1.x, dp2a_lo_su(w.x, c0.x, ab))));
+        ag = dp2a_hi_su(w.w, c3.x, dp2a_hi_su(w.z, c2.x, dp2a_hi_su(w.y, c1.x, dp2a_hi_su(w.x, c0.x, ag))));
+        ar = dp2a_lo_su(w.w, c3.y, dp2a_lo_su(w.z, c2.y, dp2a_lo_su(w.y, c1.y, dp2a_lo_su(w.x, c0.y, ar))));
+    }
+    if (COOP) __syncwarp();                              // the staging area is rewritten by the next pixel row
+    return LanczosSampler::finish(ab, ag, ar);
+}
+
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t src_smem, int x, int y, int z)
 {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
@@ -198,9 +247,9 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t s
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <bool SCORES>
-__global__ void __launch_bounds__(kTT, kTW == 4 ? (SCORES ? 4 : 5) : (SCORES ? 3 : 4))
-extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
+template <bool SCORES, bool LZ>
+__global__ void __launch_bounds__(kTT, LZ ? 4 : (kTW == 4 ? (SCORES ? 4 : 5) : (SCORES ? 3 : 4)))
+extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
     const Geom &g = a.g;
@@ -218,6 +267,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
     constexpr uint32_t kOffRaw = tiled_off_raw(SCORES);
     const uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
     const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
+    const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
 
@@ -314,9 +364,11 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 xmin = min(xmin, b.x); xmax = max(xmax, b.y); ymin = min(ymin, b.z); ymax = max(ymax, b.w);
             }
 
-            // footprint: pair records for x in [x_org, xmax], source rows [ymin, ymax + 1]
-            const int x_org = xmin & ~3, y_org = ymin;
-            const int npx = xmax - x_org + 1, rows = ymax + 2 - ymin;
+            // footprint of the taps: bilinear (ix, iy) .. (+1, +1); Lanczos4 (ix-3, iy-3) .. (ix+4, iy+4).
+            // Pair records for x in [x_org, xmax + MX1 - 1], source rows [y_org, ymax + MY1].
+            constexpr int MX0 = LZ ? 3 : 0, MX1 = LZ ? 4 : 1, MY0 = LZ ? 3 : 0, MY1 = LZ ? 4 : 1;
+            const int x_org = (xmin - MX0) & ~3, y_org = ymin - MY0;
+            const int npx = xmax + MX1 - x_org, rows = ymax + MY1 + 1 - y_org;
             const int gx0 = (3 * x_org) & ~15;                           // TMA: 16-byte aligned byte column
             const int delta = 3 * x_org - gx0;                           // 0, 4, 8 or 12
             const int need = delta + 3 * (npx + 1);                      // bytes of a row the records depend on
@@ -326,28 +378,44 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
             const int hsel = max(0, kTNumBoxH - 1 - (a.rows_max - rows) / kTBoxRows);
             const uint32_t box_rows = (uint32_t)(a.rows_max - kTBoxRows * (kTNumBoxH - 1 - hsel));
             // (coordinates outside [0, W-2] x [0, H-2] mean a wrapped tap: seam or pole)
-            const bool staged = a.stage_ok && xmin >= 0 && ymin >= 0 && xmax <= g.W - 2 && ymax <= g.H - 2 &&
-                                rows <= a.rows_max && bw <= (uint32_t)a.bw_max;
+            const bool staged = a.stage_ok && xmin - MX0 >= 0 && ymin - MY0 >= 0 && xmax + MX1 <= g.W - 1 &&
+                                ymax + MY1 <= g.H - 1 && rows <= a.rows_max && bw <= (uint32_t)a.bw_max;
             bool generic = !a.aligned;
             if (!staged) {                                               // uniform over the CTA
                 bool special = false;
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
-                    const int wx0 = wrap_idx(sat_s16(sxs[k] >> 5), g.W), wy0 = wrap_idx(sat_s16(sys[k] >> 5), g.H);
-                    const uint32_t off = (uint32_t)(wy0 * g.W + wx0) * 3u;
-                    special |= (wx0 == g.W - 1) | (wy0 == g.H - 1) | ((off & ~3u) + pitch + 12u > (uint32_t)g.H * pitch);
+                    if constexpr (LZ) {
+                        (void)LanczosSampler::make_px(sxs[k], sys[k], g, nullptr, special);
+                    } else {
+                        const int wx0 = wrap_idx(sat_s16(sxs[k] >> 5), g.W), wy0 = wrap_idx(sat_s16(sys[k] >> 5), g.H);
+                        const uint32_t off = (uint32_t)(wy0 * g.W + wx0) * 3u;
+                        special |= (wx0 == g.W - 1) | (wy0 == g.H - 1) | ((off & ~3u) + pitch + 12u > (uint32_t)g.H * pitch);
+                    }
                 }
                 generic = (__syncthreads_or(special) != 0) || !a.aligned;
             }
             if (a.tile_modes && tid == 0 && chunk == 0) atomicAdd(&a.tile_modes[staged ? 0 : (generic ? 2 : 1)], 1u);
 
             // ---- 3. per-pixel gather state: staged {upper record, lower record, w0x, w1x}, direct {off, wx, wy} --
-            const uint32_t ppitch = 3u * bw;
+            // (Lanczos4: contiguous records, 8 B per source pixel, state {record of tap (0, 0), table row offset})
+            const uint32_t ppitch = LZ ? (bw / 3u) * 8u : 3u * bw;
             uint32_t pa[kTP + 1], pa2[kTP + 1], pb[kTP + 1], pc[kTP + 1];
             pa[kTP] = pa2[kTP] = pb[kTP] = pc[kTP] = 0;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                if (staged) {
+                if constexpr (LZ) {
+                    if (staged) {
+                        const uint32_t rx = (uint32_t)((sxs[k] >> 5) - 3 - x_org), ry = (uint32_t)((sys[k] >> 5) - 3 - y_org);
+                        pa[k] = off_pairs + ry * ppitch + rx * 8u;                       // dsm-relative
+                        pb[k] = (uint32_t)((sys[k] & 31) * 32 + (sxs[k] & 31)) * 128u;
+                    } else {
+                        bool dummy = false;
+                        const LanczosSampler::Px d = LanczosSampler::make_px(sxs[k], sys[k], g, nullptr, dummy);
+                        pa[k] = d.off; pb[k] = d.info;
+                    }
+                    pa2[k] = 0; pc[k] = 0;
+                } else if (staged) {
                     const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
                     const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
                     pa[k] = dsm_s + off_pairs + ry * ppitch + (rx >> 4) * 144u + (rx & 15u) * 8u;   // shared-window address
@@ -371,7 +439,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
             uint32_t pm = 3u << (2 * (HC - 1));
 #pragma unroll
             for (int k = 0; k < kTP; ++k) {
-                if (k == HC - 1) continue;
+                if (LZ || k == HC - 1) continue;
                 const int o = k < HC ? k + 1 : k - 1;                 // the pixel this one is derived from
                 const bool same = (sxs[k] >> 5) == (sxs[o] >> 5);
                 const int adv = k < HC ? (sys[o] >> 5) - (sys[k] >> 5) : (sys[k] >> 5) - (sys[o] >> 5);
@@ -381,7 +449,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
             const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
             uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;                 // in raw buffer 0
-            uint32_t tdst0 = off_pairs + 32u * tid + 16u * (tid >> 2);
+            uint32_t tdst0 = off_pairs + 32u * tid + (LZ ? 0u : 16u * (tid >> 2));
             asm volatile("" : "+r"(tsrc0), "+r"(tdst0));                 // hoisted out of the frame loop for good
             const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
             auto issue_box = [&](int f, uint32_t b) {                    // one thread: frame f -> raw buffer b
@@ -402,7 +470,7 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                     phase ^= 1u << rb;
                     uint32_t src = tsrc0 + rb * raw_bytes, dst = tdst0;
 #pragma unroll 2
-                    for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 36u * kTT)
+                    for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += (LZ ? 32u : 36u) * kTT)
                         transform_group(dsm + src, dsm + dst);
                 }
                 // the TMA store of the previous frame must have finished reading the packed tile
@@ -418,6 +486,16 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                 uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
                 if (staged) {
                     if (f + 2 < f_end && tid == 32) issue_box(f + 2, rb);          // this frame's raw rows are consumed
+                  if constexpr (LZ) {
+#pragma unroll
+                    for (int k = 0; k < kTP; ++k) {
+                        const uint32_t pxl = lanczos_pairs<true>(dsm, pa[k], ppitch, a.lz_tab, pb[k], wst, lane);
+                        const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
+                        if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
+                        if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
+                    }
+                    if (SCORES && hvalid) halo_store(gt, tid, (uint8_t)gray_of(lanczos_pairs<false>(dsm, pa[kTP], ppitch, a.lz_tab, pb[kTP], wst, lane)));
+                  } else {
                     uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u);          // upper / lower pair record, carried down the column
                     uint2 X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);        // second chain (rows 4-7)
                     auto emit = [&](int k, const uint2 &U, const uint2 &V) {
@@ -443,21 +521,25 @@ extract_linear_tiled(const __grid_constant__ TiledArgs a, const __grid_constant_
                         const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + (pa2[kTP] - dsm_s));
                         halo_store(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
                     }
+                  }
                 } else {
+                    auto direct = [&](int k) -> uint32_t {
+                        if constexpr (LZ) {
+                            const LanczosSampler::Px d = {pa[k], pb[k]};
+                            return generic ? LanczosSampler::gather_generic(fb, d, g, a.lz_tab) : LanczosSampler::gather_fast(fb, d, g, a.lz_tab);
+                        } else {
+                            const LinearSampler::Px d = {pa[k], pb[k], pc[k]};
+                            return generic ? LinearSampler::gather_generic(fb, d, g, nullptr) : LinearSampler::gather_fast(fb, d, g, nullptr);
+                        }
+                    };
 #pragma unroll
                     for (int k = 0; k < kTP; ++k) {
-                        const LinearSampler::Px d = {pa[k], pb[k], pc[k]};
-                        const uint32_t pxl = generic ? LinearSampler::gather_generic(fb, d, g, nullptr)
-                                                     : LinearSampler::gather_fast(fb, d, g, nullptr);
+                        const uint32_t pxl = direct(k);
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     }
-                    if (SCORES && hvalid) {
-                        const LinearSampler::Px d = {pa[kTP], pb[kTP], pc[kTP]};
-                        halo_store(gt, tid, (uint8_t)gray_of(generic ? LinearSampler::gather_generic(fb, d, g, nullptr)
-                                                                      : LinearSampler::gather_fast(fb, d, g, nullptr)));
-                    }
+                    if (SCORES && hvalid) halo_store(gt, tid, (uint8_t)gray_of(direct(kTP)));
                 }
                 if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();                      // tile (+ gray halo) complete; pairs free for the next frame

@@ -322,8 +322,9 @@ def main():
     b_alg_frame = 3 * V * d * d + 3 * U + (16 * V if wl["scores"] else 0)
     kernel_ms = statistics.mean(step_ms)            # one extraction kernel per step (+2 tiny memsets with scores)
     achieved = F * b_alg_frame / (kernel_ms * 1e-3) / 1e9
-    kernel_name = ("extract_direct<LanczosSampler,%s>" if wl["mode"] == "lanczos" else
-                   {3: "extract_linear_tiled<%s>", 2: "extract_linear_staged<%s>"}.get(ex.info()["path"], "extract_direct<LinearSampler,%s>")) \
+    lz = wl["mode"] == "lanczos"
+    kernel_name = {3: "extract_tiled<%s,lanczos4>" if lz else "extract_tiled<%s,linear>", 2: "extract_linear_staged<%s>"}.get(
+        ex.info()["path"], "extract_direct<LanczosSampler,%s>" if lz else "extract_direct<LinearSampler,%s>") \
         % ("scores" if wl["scores"] else "noscores")
     traffic, traffic_src = measured_traffic(f"{args.workload}:F{F}:{kernel_name}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -86,8 +86,8 @@ SWEEP = [
 ]
 
 
-# path: 0 = auto (bilinear: the tiled TMA kernel), 1 = direct gathers, 2 = the earlier staged kernel
-@pytest.mark.parametrize("mode,interp,path", [("linear", 0, 0), ("linear", 0, 1), ("linear", 0, 2), ("lanczos", 1, 0)])
+# path: 0 = auto (the tiled TMA kernel, both interpolations), 1 = direct gathers, 2 = the earlier staged kernel (bilinear)
+@pytest.mark.parametrize("mode,interp,path", [("linear", 0, 0), ("linear", 0, 1), ("linear", 0, 2), ("lanczos", 1, 0), ("lanczos", 1, 1)])
 @pytest.mark.parametrize("cfg", SWEEP)
 def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
     H, W, d, fov, layout, n, pitch, F = cfg
@@ -96,7 +96,7 @@ def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
     R = rotations(x360, views)
     want, ws, ws2 = oracle.extract(frames, R, d, fov, interp)
     with x360.Extractor(H, W, d, fov, R, mode, path=path) as ex:
-        assert ex.info()["path"] == (1 if (interp or path == 1) else (2 if path == 2 else 3))
+        assert ex.info()["path"] == (1 if path == 1 else (2 if path == 2 else 3))
         got, s, s2 = ex.extract_sums(frames)
         modes = ex.tile_modes()
         got_ns, none = ex.extract(frames, want_scores=False)      # the no-score kernel variant
