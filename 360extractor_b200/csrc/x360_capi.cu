@@ -143,16 +143,20 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // ---- tiled path (x360_tiled.cuh) ---------------------------------------------------------------
 typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 
-tiled_fn pick_tiled(bool scores, bool lanczos)
+tiled_fn pick_tiled(bool scores, bool lanczos, int tp)
 {
-    if (lanczos) return scores ? extract_tiled<true, true> : extract_tiled<false, true>;
-    return scores ? extract_tiled<true, false> : extract_tiled<false, false>;
+    if (tp == 4) {
+        if (lanczos) return scores ? extract_tiled<true, true, 4> : extract_tiled<false, true, 4>;
+        return scores ? extract_tiled<true, false, 4> : extract_tiled<false, false, 4>;
+    }
+    if (lanczos) return scores ? extract_tiled<true, true, 8> : extract_tiled<false, true, 8>;
+    return scores ? extract_tiled<true, false, 8> : extract_tiled<false, false, 8>;
 }
 
 // load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W];
 // store box {96, 32, 1} of uint8 [F*V][oh][3 ow]
 bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max, bool with_in, uint8_t *out, int FV, int oh,
-                       int ow, bool with_out, TiledMaps *tm)
+                       int ow, int tile_h, bool with_out, TiledMaps *tm)
 {
     encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
@@ -172,7 +176,7 @@ bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max,
     if (with_out) {
         const cuuint64_t dims[3] = {(cuuint64_t)ow * 3, (cuuint64_t)oh, (cuuint64_t)FV};
         const cuuint64_t strides[2] = {(cuuint64_t)ow * 3, (cuuint64_t)ow * 3 * oh};
-        const cuuint32_t box[3] = {(cuuint32_t)(kTile * 3), (cuuint32_t)kTile, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)(kTile * 3), (cuuint32_t)tile_h, 1};
         if (enc(&tm->out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)out, dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -242,59 +246,68 @@ HostUnits build_units(const double *R, int V, int W, bool share)
     return h;
 }
 
-// Host estimate of the per-tile source footprints (9 sample points of each 34x34 tile incl. halo) ->
-// the staging capacity (footprint rows, raw bytes per row) that maximises
-//   (fraction of tiles that fit) x (throughput factor of the CTAs/SM the shared-memory size allows).
-// Seam-wrapping and pole tiles never fit and go direct whatever the capacity.
-void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, int *rows_out, int *bw_out)
+// Host estimate of the per-tile source footprints (9 sample points of each tile incl. halo) -> the tile
+// height (32 or 16 output rows) and staging capacity (footprint rows, raw bytes per row) that maximise
+//   (throughput factor of the CTAs/SM the shared-memory size allows) x (factor of the tile height)
+//   / (cost of the tiles that fit + 3 x the tiles that do not: those go through the direct gathers).
+// Seam-wrapping and pole tiles never fit whatever the capacity.
+void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, int *rows_out, int *bw_out, int *tile_h_out)
 {
-    std::vector<int> rows, bws;
-    size_t total = 0;
-    for (int v = 0; v < V; ++v) {
-        const double *Rv = R + 9 * v;
-        for (int ty = 0; ty < g.tiles_y; ++ty)
-            for (int tx = 0; tx < g.tiles_x; ++tx) {
-                ++total;
-                int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-                for (int j = 0; j < 3; ++j)
-                    for (int i = 0; i < 3; ++i) {
-                        const double x = std::min<double>(std::max(0, tx * kTile - 1 + i * 33 / 2), g.ow - 1);
-                        const double y = std::min<double>(std::max(0, ty * kTile - 1 + j * 33 / 2), g.oh - 1);
-                        const double xn = (x - g.cx) / g.f, yn = (y - g.cy) / g.f;
-                        const double v0 = xn * Rv[0] + yn * Rv[1] + Rv[2], v1 = xn * Rv[3] + yn * Rv[4] + Rv[5],
-                                     v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
-                        const double u = (std::atan2(v0, v2) / (2.0 * 3.14159265358979323846) + 0.5) * g.W;
-                        const double w = (std::asin(v1 / std::sqrt(v0 * v0 + v1 * v1 + v2 * v2)) / 3.14159265358979323846 + 0.5) * g.H;
-                        const int ix = (int)std::floor(u), iy = (int)std::floor(w);
-                        xmin = std::min(xmin, ix); xmax = std::max(xmax, ix);
-                        ymin = std::min(ymin, iy); ymax = std::max(ymax, iy);
-                    }
-                if (xmax - xmin > g.W / 2) continue;                      // wraps the seam: never staged
-                const int m = lanczos ? 7 : 0;                            // 8x8 taps: 3 before, 4 after
-                rows.push_back(ymax - ymin + 3 + m);
-                const int npx = xmax - (xmin & ~3) + 2 + m;
-                bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);        // worst alignment
-            }
-    }
     // measured on cfg2 (B200): 5 CTAs/SM 1.0, 4 CTAs 0.92; fewer CTAs hide less latency
     static const double occ_factor[9] = {0.0, 0.35, 0.6, 0.8, 0.92, 1.0, 1.04, 1.06, 1.08};
     double best = -1.0;
-    int best_rows = 40, best_bw = 144;
-    for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
-        for (int r = 24; r <= 96; r += kTBoxRows) {
-            const size_t smem = tiled_smem_bytes(r, bw, false, lanczos) + 1024;
-            if (smem > 110 * 1024) continue;
-            int occ = (int)((227 * 1024) / smem);
-            occ = occ > 8 ? 8 : occ;
-            size_t fit = 0;
-            for (size_t i = 0; i < rows.size(); ++i) fit += (rows[i] <= r && bws[i] <= bw);
-            const double cover = total ? (double)fit / (double)total : 0.0;
-            // tiles that do not fit run ~3x slower through the direct gathers
-            const double score = occ_factor[occ] / (cover + 3.0 * (1.0 - cover));
-            if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; }
+    int best_rows = 40, best_bw = 144, best_th = 32;
+    const int m = lanczos ? 7 : 0;                                        // 8x8 taps: 3 before, 4 after
+    int forced_th = 0;
+    if (const char *e = getenv("X360_TILED_TH")) forced_th = atoi(e);
+    for (int th = 32; th >= 16; th -= 16) {
+        if (forced_th && forced_th != th) continue;
+        std::vector<int> rows, bws;
+        size_t total = 0;
+        const int tiles_y = (g.oh + th - 1) / th;
+        for (int v = 0; v < V; ++v) {
+            const double *Rv = R + 9 * v;
+            for (int ty = 0; ty < tiles_y; ++ty)
+                for (int tx = 0; tx < g.tiles_x; ++tx) {
+                    ++total;
+                    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+                    for (int j = 0; j < 3; ++j)
+                        for (int i = 0; i < 3; ++i) {
+                            const double x = std::min<double>(std::max(0, tx * kTile - 1 + i * 33 / 2), g.ow - 1);
+                            const double y = std::min<double>(std::max(0, ty * th - 1 + j * (th + 1) / 2), g.oh - 1);
+                            const double xn = (x - g.cx) / g.f, yn = (y - g.cy) / g.f;
+                            const double v0 = xn * Rv[0] + yn * Rv[1] + Rv[2], v1 = xn * Rv[3] + yn * Rv[4] + Rv[5],
+                                         v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
+                            const double u = (std::atan2(v0, v2) / (2.0 * 3.14159265358979323846) + 0.5) * g.W;
+                            const double w = (std::asin(v1 / std::sqrt(v0 * v0 + v1 * v1 + v2 * v2)) / 3.14159265358979323846 + 0.5) * g.H;
+                            const int ix = (int)std::floor(u), iy = (int)std::floor(w);
+                            xmin = std::min(xmin, ix); xmax = std::max(xmax, ix);
+                            ymin = std::min(ymin, iy); ymax = std::max(ymax, iy);
+                        }
+                    if (xmax - xmin > g.W / 2) continue;                  // wraps the seam: never staged
+                    rows.push_back(ymax - ymin + 3 + m);
+                    const int npx = xmax - (xmin & ~3) + 2 + m;
+                    bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);    // worst alignment
+                }
         }
+        // 16-row tiles pay the per-frame overheads over half the pixels and reuse fewer records (cfg2: 0.85)
+        const double th_factor = th == 32 ? 1.0 : 0.85;
+        for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
+            for (int r = 24; r <= 96; r += kTBoxRows) {
+                const size_t smem = tiled_smem_bytes(r, bw, false, lanczos, th) + 1024;
+                if (smem > 110 * 1024) continue;
+                int occ = (int)((227 * 1024) / smem);
+                occ = occ > 8 ? 8 : occ;
+                size_t fit = 0;
+                for (size_t i = 0; i < rows.size(); ++i) fit += (rows[i] <= r && bws[i] <= bw);
+                const double cover = total ? (double)fit / (double)total : 0.0;
+                const double score = th_factor * occ_factor[occ] / (cover + 3.0 * (1.0 - cover));
+                if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; best_th = th; }
+            }
+    }
     *rows_out = best_rows;
     *bw_out = best_bw;
+    *tile_h_out = best_th;
 }
 
 }  // namespace
@@ -310,7 +323,7 @@ struct x360_plan {
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
     unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
     // tiled path
-    int t_bw = 144, t_rows = 40, n_units = 0;
+    int t_bw = 144, t_rows = 40, t_th = 32, n_units = 0;   // staging capacity, tile height (32 or 16)
     size_t t_smem[2] = {0, 0};           // dynamic shared memory without / with scores
     TiledUnit *d_units = nullptr;
     int *d_unit_view = nullptr;
@@ -329,7 +342,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4), kTT, pl->t_smem[scores ? 1 : 0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th / kTW), kTT, pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -366,15 +379,16 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.V = pl->p.n_views;
     a.rows_max = pl->t_rows;
     a.bw_max = pl->t_bw;
+    a.tiles_y = (g.oh + pl->t_th - 1) / pl->t_th;
     a.aligned = ((uintptr_t)frames % 4 == 0) && (g.W % 4 == 0);
     a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= pl->t_rows && g.W * 3 >= 256;
-    a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= kTile;
+    a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= pl->t_th;
     if (getenv("X360_NO_TMA_STORE") && atoi(getenv("X360_NO_TMA_STORE"))) a.store_ok = 0;
 
     // frames per chunk: enough work items for the dynamic scheduler to balance the grid, but as many
     // frames per item as possible (the map of a tile is evaluated once per item)
     const int cap = plan_grid(pl, scores);
-    const long long tiles = (long long)g.tiles_x * g.tiles_y;
+    const long long tiles = (long long)g.tiles_x * a.tiles_y;
     long long want_chunks = (6LL * cap + pl->n_units * tiles - 1) / (pl->n_units * tiles);
     if (want_chunks < 1) want_chunks = 1;
     if (want_chunks > n_frames) want_chunks = n_frames;
@@ -390,7 +404,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     TiledMaps tms;
     memset(&tms, 0, sizeof tms);
     if ((a.stage_ok || a.store_ok) &&
-        !encode_tiled_maps(frames, n_frames, g.H, g.W, pl->t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, a.store_ok != 0, &tms)) {
+        !encode_tiled_maps(frames, n_frames, g.H, g.W, pl->t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, pl->t_th, a.store_ok != 0, &tms)) {
         a.stage_ok = 0;                                   // every tile goes direct, byte stores
         a.store_ok = 0;
     }
@@ -400,7 +414,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4)<<<grid, kTT, pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
+    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th / kTW)<<<grid, kTT, pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -423,7 +437,7 @@ int x360_lanczos4_table(int16_t *out)
 double x360_focal(int32_t out_w, double fov_deg) { return focal_of(out_w, fov_deg); }
 
 int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,
-                      int32_t *rows_max, int32_t *bw_max)
+                      int32_t *rows_max, int32_t *bw_max, int32_t *tile_h)
 {
     if (!params || !params->R || params->n_views < 1) return fail(X360_E_INVALID, "null argument");
     if (params->struct_size != (int32_t)sizeof(x360_params)) return fail(X360_E_INVALID, "x360_params.struct_size mismatch");
@@ -437,11 +451,12 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
             if (unit_of_view) unit_of_view[h.view[e]] = (int32_t)u;
             if (shift_px) shift_px[h.view[e]] = h.shift[e];
         }
-    int rows = 0, bw = 0;
+    int rows = 0, bw = 0, th = 0;
     choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
-                    params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw);
+                    params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw, &th);
     if (rows_max) *rows_max = rows;
     if (bw_max) *bw_max = bw;
+    if (tile_h) *tile_h = th;
     return X360_OK;
 }
 
@@ -480,16 +495,17 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
                : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
     if (pl->path == X360_PATH_TILED) {
         // staging capacity from a host survey of the tiles' footprints
-        int rows = 40, bw = 144;
-        choose_capacity(pl->g, params->R, params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw);
+        int rows = 40, bw = 144, th = 32;
+        choose_capacity(pl->g, params->R, params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw, &th);
+        pl->t_th = th;
         if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
         if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-        while (rows > 24 && tiled_smem_bytes(rows, bw, true, params->interp == X360_INTERP_LANCZOS4) > 100 * 1024) rows -= kTBoxRows;
+        while (rows > 24 && tiled_smem_bytes(rows, bw, true, params->interp == X360_INTERP_LANCZOS4, th) > 110 * 1024) rows -= kTBoxRows;
         pl->t_bw = bw;
         pl->t_rows = rows;
         for (int sc = 0; sc < 2; ++sc) {
-            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, params->interp == X360_INTERP_LANCZOS4);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, params->interp == X360_INTERP_LANCZOS4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, params->interp == X360_INTERP_LANCZOS4, th);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, params->interp == X360_INTERP_LANCZOS4, th / kTW), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];
                 delete pl;

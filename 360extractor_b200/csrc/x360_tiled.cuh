@@ -42,13 +42,10 @@
 
 namespace x360 {
 
-#ifndef X360_TILED_PX
-#define X360_TILED_PX 8
-#endif
-constexpr int kTP = X360_TILED_PX;    // output pixels (rows) per thread: warp w owns tile rows kTP w .. kTP w + kTP - 1
-constexpr int kTT = kTile * kTile / kTP;   // threads per CTA (128: 4 warps)
-constexpr int kTW = kTT / 32;         // warps per CTA
-static_assert(kTP == 8 || kTP == 4, "the gather is written out for 8 or 4 rows per thread");
+constexpr int kTT = 128;              // threads per CTA: 4 warps, lanes along x
+constexpr int kTW = kTT / 32;         // warps per CTA; warp w owns tile rows TP w .. TP w + TP - 1
+// TP = output pixels (rows) per thread: 8 (32x32 tiles) or 4 (32x16 tiles, for geometries whose
+// footprints are too large to keep enough CTAs per SM with 32 rows)
 constexpr int kTBoxRows = 8;          // granularity of the footprint row capacity
 constexpr int kTNumBoxW = 5;          // load box widths 48, 96, 144, 192, 240 bytes (16, 32, ... source pixels)
 constexpr int kTNumBoxH = 3;          // load box heights rows_max - 16, rows_max - 8, rows_max
@@ -57,7 +54,7 @@ constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
 
 struct TiledMaps {
     CUtensorMap in[kTNumBox];         // uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]
-    CUtensorMap out;                  // uint8 [F*V][oh][3 ow], box {96, 32, 1}
+    CUtensorMap out;                  // uint8 [F*V][oh][3 ow], box {96, tile height, 1}
 };
 
 // One view unit: `n` views starting at `first` in the (view id, shift) tables share a map.
@@ -83,6 +80,7 @@ struct TiledArgs {
     int stage_ok;                     // TMA loads possible (frame base and pitch 16-B aligned)
     int store_ok;                     // TMA stores possible (out base and pitch 16-B aligned)
     int rows_max, bw_max;             // staging capacity: footprint rows, raw bytes per footprint row (48 k)
+    int tiles_y;                      // tile rows per view (tile height 32 or 16)
 };
 
 struct TiledCtrl {
@@ -103,21 +101,100 @@ struct TiledCtrl {
 //        r * 3 bw + (x >> 4) * 144 + (x & 15) * 8.
 constexpr uint32_t kOffCtl = 0;
 constexpr uint32_t kOffTile = 128;
-constexpr uint32_t kOffU0 = kOffTile + kTile * kTile * 3;
-constexpr uint32_t kOffSy = kOffU0 + kTile * kTile * 8;
-constexpr uint32_t kOffGray = kOffSy + kTile * kTile * 4;
-__host__ __device__ constexpr uint32_t tiled_off_raw(bool scores) { return scores ? ((kOffGray + (uint32_t)sizeof(GrayTile) + 127u) & ~127u) : kOffGray; }
 static_assert(sizeof(TiledCtrl) <= 128, "ctrl block");
-static_assert(kOffGray % 128 == 0, "raw buffers must be 128-byte aligned");
+
+// gray tile (TH rows + 1-px halo): rows -1..TH as compact 32-B rows, left / right halo columns apart
+template <int TH> struct TGray {
+    uint8_t g[TH + 2][kTile];
+    uint8_t hl[TH];
+    uint8_t hr[TH];
+};
+
+__host__ __device__ constexpr uint32_t tiled_off_u0(int th) { return kOffTile + (uint32_t)th * kTile * 3; }
+__host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return tiled_off_u0(th) + (uint32_t)th * kTile * 8; }
+__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 4; }
+__host__ __device__ constexpr uint32_t tiled_off_raw(bool scores, int th)
+{
+    return scores ? ((tiled_off_gray(th) + (uint32_t)((th + 2) * kTile + 2 * th) + 127u) & ~127u) : tiled_off_gray(th);
+}
+static_assert(tiled_off_gray(32) % 128 == 0 && tiled_off_gray(16) % 128 == 0, "raw buffers must be 128-byte aligned");
 
 // one raw buffer: rows_max x bw_max, rounded up to the TMA destination alignment
 __host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 127u) & ~127u; }
 __host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * 3 * bw_max) + 16u + 15u) & ~15u; }
-__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos)
+__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th)
 {
-    // ... | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
-    return (size_t)tiled_off_raw(scores) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max) +
-           (lanczos ? (size_t)(kTile * kTile / X360_TILED_PX / 32) * 32 * 144 : 0);
+    // ctrl | packed tile | map_x | map_y | [gray] | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
+    return (size_t)tiled_off_raw(scores, th) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max) +
+           (lanczos ? (size_t)kTW * 32 * 144 : 0);
+}
+
+// Halo pixel of thread `tid`: 0-31 top, 32-63 bottom, then TH left, TH right.  False if tid has none.
+template <int TH> __device__ __forceinline__ bool halo_coords_t(int tid, int x0, int y0, int &hx, int &hy)
+{
+    if (tid < 32) { hx = x0 + tid; hy = y0 - 1; }
+    else if (tid < 64) { hx = x0 + tid - 32; hy = y0 + TH; }
+    else if (tid < 64 + TH) { hx = x0 - 1; hy = y0 + tid - 64; }
+    else if (tid < 64 + 2 * TH) { hx = x0 + kTile; hy = y0 + tid - 64 - TH; }
+    else return false;
+    return true;
+}
+template <int TH> __device__ __forceinline__ void halo_store_t(TGray<TH> &t, int tid, uint8_t v)
+{
+    if (tid < 32) t.g[0][tid] = v;
+    else if (tid < 64) t.g[TH + 1][tid - 32] = v;
+    else if (tid < 64 + TH) t.hl[tid - 64] = v;
+    else t.hr[tid - 64 - TH] = v;
+}
+template <int TH> __device__ __forceinline__ int gray_at_t(const TGray<TH> &t, int ly, int lx)
+{
+    if (lx < 0) return t.hl[ly];
+    if (lx >= kTile) return t.hr[ly];
+    return t.g[ly + 1][lx];
+}
+// Laplacian sums of the tile (image_utils.py:27, reflect-101 borders): partial (sum L, sum L^2) of virtual
+// thread vt in [0, 8 TH): one 4-pixel word each on full tiles (dp4a), a strided loop on partial tiles.
+template <int TH> __device__ __forceinline__ void laplacian_partial_t(const TGray<TH> &t, const Geom &g, int x0, int y0, bool full,
+                                                                      int vt, int &pl, unsigned &pl2)
+{
+    pl = 0;
+    pl2 = 0;
+    if (full) {
+        const int ly = vt >> 3, wx = vt & 7;
+        const uint32_t C = *reinterpret_cast<const uint32_t *>(&t.g[ly + 1][wx * 4]);
+        uint32_t U = *reinterpret_cast<const uint32_t *>(&t.g[ly][wx * 4]);
+        uint32_t D = *reinterpret_cast<const uint32_t *>(&t.g[ly + 2][wx * 4]);
+        uint32_t l = (wx > 0) ? t.g[ly + 1][wx * 4 - 1] : t.hl[ly];
+        uint32_t r = (wx < 7) ? t.g[ly + 1][wx * 4 + 4] : t.hr[ly];
+        if (y0 + ly == 0) U = D;                                   // reflect-101: g[-1] = g[1], g[n] = g[n-2]
+        if (y0 + ly == g.oh - 1) D = U;
+        if (x0 + wx * 4 == 0) l = (C >> 8) & 0xffu;
+        if (x0 + wx * 4 + 3 == g.ow - 1) r = (C >> 16) & 0xffu;
+        const uint32_t Lw = __byte_perm(C, l, 0x2104);             // [l, c0, c1, c2]
+        const uint32_t Rw = __byte_perm(C, r, 0x4321);             // [c1, c2, c3, r]
+        constexpr uint32_t kA = 0x0001fc01u;                       // [ 1, -4,  1,  0]
+        constexpr uint32_t kB = 0x01fc0100u;                       // [ 0,  1, -4,  1]
+        const int L0 = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
+        const int L1 = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
+        const int L2 = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
+        const int L3 = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
+        pl = L0 + L1 + L2 + L3;
+        pl2 = (unsigned)(L0 * L0) + (unsigned)(L1 * L1) + (unsigned)(L2 * L2) + (unsigned)(L3 * L3);
+    } else {
+        for (int i = vt; i < TH * kTile; i += 8 * TH) {
+            const int ly = i >> 5, lx = i & 31;
+            const int x = x0 + lx, y = y0 + ly;
+            if (x >= g.ow || y >= g.oh) continue;
+            const int yu = (y == 0) ? ((g.oh > 1) ? 1 : 0) : y - 1;
+            const int yd = (y == g.oh - 1) ? ((g.oh > 1) ? g.oh - 2 : 0) : y + 1;
+            const int xl = (x == 0) ? ((g.ow > 1) ? 1 : 0) : x - 1;
+            const int xr = (x == g.ow - 1) ? ((g.ow > 1) ? g.ow - 2 : 0) : x + 1;
+            const int c = gray_at_t(t, ly, lx);
+            const int L = gray_at_t(t, yu - y0, lx) + gray_at_t(t, yd - y0, lx) + gray_at_t(t, ly, xl - x0) + gray_at_t(t, ly, xr - x0) - 4 * c;
+            pl += L;
+            pl2 += (unsigned)(L * L);
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a16x2, uint32_t b, uint32_t c)
@@ -247,8 +324,8 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t s
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <bool SCORES, bool LZ>
-__global__ void __launch_bounds__(kTT, LZ ? 4 : (kTW == 4 ? (SCORES ? 4 : 5) : (SCORES ? 3 : 4)))
+template <bool SCORES, bool LZ, int TP>
+__global__ void __launch_bounds__(kTT, LZ ? (TP == 4 ? 5 : 4) : (TP == 4 ? (SCORES ? 6 : 7) : (SCORES ? 4 : 5)))
 extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
@@ -259,12 +336,15 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     const size_t view_bytes = (size_t)g.oh * g.ow * 3;
     const size_t opitch = (size_t)g.ow * 3;
 
+    static_assert(TP == 8 || TP == 4, "the gather is written out for 8 or 4 rows per thread");
+    constexpr int kTP = TP;
+    constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
     uint8_t *const otile = dsm + kOffTile;
-    double *const u0s = reinterpret_cast<double *>(dsm + kOffU0);
-    int *const sy_s = reinterpret_cast<int *>(dsm + kOffSy);
-    GrayTile &gt = *reinterpret_cast<GrayTile *>(dsm + kOffGray);
-    constexpr uint32_t kOffRaw = tiled_off_raw(SCORES);
+    double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(TH));
+    int *const sy_s = reinterpret_cast<int *>(dsm + tiled_off_sy(TH));
+    TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + tiled_off_gray(TH));
+    constexpr uint32_t kOffRaw = tiled_off_raw(SCORES, TH);
     const uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
     const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
     const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
@@ -280,7 +360,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     uint32_t pack_sel = q == 0 ? 0x4210u : (q == 1 ? 0x5421u : 0x6542u);
     uint32_t my_word = (uint32_t)(warp * kTP) * (kTile * 3) + (uint32_t)((lane >> 2) * 3 + q) * 4u;
     asm volatile("" : "+r"(pack_sel), "+r"(my_word));      // keep both in registers: rematerialising them costs more than the gather
-    const int tiles_per_view = g.tiles_x * g.tiles_y;
+    const int tiles_per_view = g.tiles_x * a.tiles_y;
     const double Wd = (double)g.W;
 
     for (;;) {
@@ -294,9 +374,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
         const TiledUnit unit = a.units[u];
         const int chunk = local / tiles_per_view, tile = local - chunk * tiles_per_view;
         const int ty = tile / g.tiles_x;
-        const int x0 = (tile - ty * g.tiles_x) * kTile, y0 = ty * kTile;
+        const int x0 = (tile - ty * g.tiles_x) * kTile, y0 = ty * TH;
         const int f_begin = chunk * a.FG, f_end = min(a.F, f_begin + a.FG);
-        const bool full = (x0 + kTile <= g.ow) && (y0 + kTile <= g.oh);
+        const bool full = (x0 + kTile <= g.ow) && (y0 + TH <= g.oh);
 
         // ---- 1. the unit's map for this tile, to shared memory: fp64 map_x, Q5 map_y -------------
         double hu0 = 0.0;
@@ -312,10 +392,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 u0s[k * kTT + tid] = uf;
                 sy_s[k * kTT + tid] = q5_of(my);
             }
-            if (SCORES && tid < 128) {
-                int hx, hy;
-                halo_coords(tid, x0, y0, hx, hy);
-                hvalid = (hx >= 0 && hx < g.ow && hy >= 0 && hy < g.oh);
+            if (SCORES) {
+                int hx = -1, hy = -1;
+                hvalid = halo_coords_t<TH>(tid, x0, y0, hx, hy) && hx >= 0 && hx < g.ow && hy >= 0 && hy < g.oh;
                 if (hvalid) {
                     float my;
                     map_f64(R, g, hx, hy, hu0, my);
@@ -494,7 +573,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     }
-                    if (SCORES && hvalid) halo_store(gt, tid, (uint8_t)gray_of(lanczos_pairs<false>(dsm, pa[kTP], ppitch, a.lz_tab, pb[kTP], wst, lane)));
+                    if (SCORES && hvalid) halo_store_t<TH>(gt, tid, (uint8_t)gray_of(lanczos_pairs<false>(dsm, pa[kTP], ppitch, a.lz_tab, pb[kTP], wst, lane)));
                   } else {
                     uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u);          // upper / lower pair record, carried down the column
                     uint2 X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);        // second chain (rows 4-7)
@@ -519,7 +598,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     if (SCORES && hvalid) {
                         const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + (pa[kTP] - dsm_s));
                         const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + (pa2[kTP] - dsm_s));
-                        halo_store(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
+                        halo_store_t<TH>(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
                     }
                   }
                 } else {
@@ -539,7 +618,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     }
-                    if (SCORES && hvalid) halo_store(gt, tid, (uint8_t)gray_of(direct(kTP)));
+                    if (SCORES && hvalid) halo_store_t<TH>(gt, tid, (uint8_t)gray_of(direct(kTP)));
                 }
                 if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();                      // tile (+ gray halo) complete; pairs free for the next frame
@@ -547,9 +626,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (a.store_ok) {
                     if (tid == 0) tma_store_tile(&tms.out, otile_s, x0 * 3, y0, f * a.V + v);
                 } else {
-                    const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(kTile, g.oh - y0);
+                    const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(TH, g.oh - y0);
                     uint8_t *out_view = a.out + ((size_t)f * a.V + v) * view_bytes;
-                    for (int i = tid; i < kTile * kTile * 3; i += kTT) {
+                    for (int i = tid; i < TH * kTile * 3; i += kTT) {
                         const int row = i / (kTile * 3), bb = i - row * (kTile * 3);
                         if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = otile[i];
                     }
@@ -557,9 +636,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (SCORES) {
                     int pl = 0; unsigned pl2 = 0;
 #pragma unroll
-                    for (int h = 0; h < 256 / kTT; ++h) {
+                    for (int h = 0; h < 8 * TH / kTT; ++h) {
                         int l1; unsigned l2;
-                        laplacian_partial(gt, g, x0, y0, full, tid + h * kTT, l1, l2);
+                        laplacian_partial_t<TH>(gt, g, x0, y0, full, tid + h * kTT, l1, l2);
                         pl += l1; pl2 += l2;
                     }
                     pl = __reduce_add_sync(0xffffffffu, pl);

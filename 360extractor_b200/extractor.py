@@ -30,7 +30,7 @@ def scores_from_sums(sum_lap, sum_lap2, n_pixels: int) -> np.ndarray:
     return s2 / float(n_pixels) - mean * mean
 
 
-def plan_preview(src_h, src_w, out_res, fov_deg, R, *, out_h=None):
+def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *, out_h=None):
     """Host-only view of how the tiled bilinear path organises a job (no device needed): the view units
     that share one map evaluation (views differing only by a yaw), each view's map_x shift inside its
     unit, and the shared-memory staging capacity chosen from the tiles' source footprints."""
@@ -40,15 +40,16 @@ def plan_preview(src_h, src_w, out_res, fov_deg, R, *, out_h=None):
     p.src_w, p.src_h = int(src_w), int(src_h)
     p.out_w, p.out_h = int(out_res), int(out_h if out_h is not None else out_res)
     p.fov_deg = float(fov_deg)
+    p.interp = interp_code(interpolation_mode)
     p.n_views = int(R.shape[0])
     p.R = R.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-    n_units, rows, bw = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    n_units, rows, bw, th = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     unit = np.zeros(p.n_views, np.int32)
     shift = np.zeros(p.n_views, np.float64)
     check(lib().x360_plan_preview(ctypes.byref(p), ctypes.byref(n_units), unit.ctypes.data, shift.ctypes.data,
-                                  ctypes.byref(rows), ctypes.byref(bw)))
+                                  ctypes.byref(rows), ctypes.byref(bw), ctypes.byref(th)))
     return {"n_units": n_units.value, "unit_of_view": unit.tolist(), "shift_px": shift.tolist(),
-            "rows_max": rows.value, "bw_max": bw.value}
+            "rows_max": rows.value, "bw_max": bw.value, "tile_h": th.value}
 
 
 class Extractor:

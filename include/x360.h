@@ -140,10 +140,12 @@ double x360_focal(int32_t out_w, double fov_deg);
  *   shift_px      [n_views] map_x shift of the view relative to its unit's first view, in source pixels [0, W)
  *   rows_max, bw_max  staging capacity chosen from a survey of the tiles' source footprints
  *                 (footprint rows; raw bytes per footprint row, a multiple of 48)
+ *   tile_h        output tile height the plan works in: 32, or 16 where 32-row footprints would leave too
+ *                 few CTAs per SM (tiles are 32 pixels wide)
  * Any output pointer may be NULL.
  */
 int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,
-                      int32_t *rows_max, int32_t *bw_max);
+                      int32_t *rows_max, int32_t *bw_max, int32_t *tile_h);
 
 /* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
 int x360_host_alloc(size_t bytes, void **out_ptr);
