@@ -86,7 +86,7 @@ struct TiledArgs {
 struct TiledCtrl {
     int wbb[kTW][4];                  // per-warp footprint bounding boxes (16-B aligned rows)
     unsigned long long mbar[2];       // one per raw buffer
-    long long sums[2];
+    int wsum[kTW][2];                 // per-warp (sum L, sum L^2) of the current frame's tile (exact in 32 bits)
     int item;
 };
 
@@ -435,7 +435,6 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
             ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
             if (lane == 0) *reinterpret_cast<int4 *>(ctl.wbb[warp]) = make_int4(xmin, xmax, ymin, ymax);
-            if (tid == 0) { ctl.sums[0] = 0; ctl.sums[1] = 0; }
             __syncthreads();
 #pragma unroll
             for (int w = 0; w < kTW; ++w) {
@@ -556,9 +555,11 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncthreads();                      // pairs ready, raw consumed, tile buffer free
                 if (SCORES && tid == 0 && f > f_begin) {
-                    atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f - 1) * a.V + v], (unsigned long long)ctl.sums[0]);
-                    atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f - 1) * a.V + v], (unsigned long long)ctl.sums[1]);
-                    ctl.sums[0] = 0; ctl.sums[1] = 0;
+                    long long s1 = 0, s2 = 0;                 // every warp's partial of frame f-1 is in (barrier above)
+#pragma unroll
+                    for (int w = 0; w < kTW; ++w) { s1 += ctl.wsum[w][0]; s2 += (unsigned)ctl.wsum[w][1]; }
+                    atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f - 1) * a.V + v], (unsigned long long)s1);
+                    atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f - 1) * a.V + v], (unsigned long long)s2);
                 }
                 uint32_t obase = kOffTile + my_word;
                 asm volatile("" : "+r"(obase));
@@ -644,15 +645,18 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     pl = __reduce_add_sync(0xffffffffu, pl);
                     pl2 = __reduce_add_sync(0xffffffffu, pl2);
                     if (lane == 0) {
-                        atomicAdd((unsigned long long *)&ctl.sums[0], (unsigned long long)(long long)pl);
-                        atomicAdd((unsigned long long *)&ctl.sums[1], (unsigned long long)pl2);
+                        ctl.wsum[warp][0] = pl;               // |sum L| <= 1020 * 256, sum L^2 <= 1020^2 * 256 < 2^32
+                        ctl.wsum[warp][1] = (int)pl2;
                     }
                 }
             }
             __syncthreads();                           // every warp's partial of the last frame is in
             if (SCORES && tid == 0) {
-                atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f_end - 1) * a.V + v], (unsigned long long)ctl.sums[0]);
-                atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f_end - 1) * a.V + v], (unsigned long long)ctl.sums[1]);
+                long long s1 = 0, s2 = 0;
+#pragma unroll
+                for (int w = 0; w < kTW; ++w) { s1 += ctl.wsum[w][0]; s2 += (unsigned)ctl.wsum[w][1]; }
+                atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f_end - 1) * a.V + v], (unsigned long long)s1);
+                atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f_end - 1) * a.V + v], (unsigned long long)s2);
             }
         }
     }

@@ -46,6 +46,10 @@ WORKLOADS = {
                  desc="7680x3840 -> fibonacci 20 views pitch -20 1920^2 Lanczos4"),
     "cfg4": dict(W=7680, H=3840, layout="cube", n=6, pitch=0, active=None, d=1920, fov=90, mode="linear", scores=True, F=32,
                  desc="7680x3840 clip -> cube 6x1920^2 bilinear + fused blur score"),
+    "cfg4_noscore": dict(W=7680, H=3840, layout="cube", n=6, pitch=0, active=None, d=1920, fov=90, mode="linear", scores=False, F=32,
+                 desc="7680x3840 clip -> cube 6x1920^2 bilinear (diagnostic: cfg4 without the blur score)"),
+    "cfg4_ring": dict(W=7680, H=3840, layout="ring", n=6, pitch=0, active=None, d=1920, fov=90, mode="linear", scores=True, F=32,
+                 desc="7680x3840 clip -> ring 6x1920^2 bilinear + blur score (diagnostic: cfg4 without the pole faces)"),
     "cfg5": dict(W=11520, H=5760, layout="ring", n=12, pitch=0, active=[0, 3, 6, 9], d=2048, fov=90, mode="lanczos", scores=False, F=1,
                  desc="11520x5760 -> ring 12 (active 0,3,6,9) 2048^2 Lanczos4"),
 }
