@@ -490,7 +490,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->p.R = nullptr;
     pl->g = make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg);
     pl->sm_count = prop.multiProcessorCount;
-    pl->chunk = params->max_batch > 0 ? params->max_batch : 8;
+    pl->chunk = params->max_batch > 0 ? params->max_batch : 2;
     pl->path = params->path == X360_PATH_DIRECT ? X360_PATH_DIRECT
                : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
     if (pl->path == X360_PATH_TILED) {

@@ -56,7 +56,7 @@ class Extractor:
     """Plan wrapper.  ``R`` is fp64 ``[V][3][3]`` from ``GeometryProcessor.get_rotation_matrix``."""
 
     def __init__(self, src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *,
-                 out_h=None, device=0, max_batch=8, path=_capi.PATH_AUTO):
+                 out_h=None, device=0, max_batch=0, path=_capi.PATH_AUTO):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
         self.src_h, self.src_w = int(src_h), int(src_w)
         self.out_w = int(out_res)

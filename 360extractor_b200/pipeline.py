@@ -32,7 +32,7 @@ class ViewResult:
 class ExtractionSession:
     """One job: settings dict + source size -> plan; ``process(frames)`` -> kept views."""
 
-    def __init__(self, settings: dict, src_h: int, src_w: int, device: int = 0, max_batch: int = 8):
+    def __init__(self, settings: dict, src_h: int, src_w: int, device: int = 0, max_batch: int = 0):
         self.settings = settings
         self.out_res = settings.get("resolution", 2048)                 # job.py:40
         self.fov = settings.get("fov", 90)                              # processor.py:166

@@ -264,7 +264,7 @@ def main():
     views = pkg.GeometryProcessor.generate_views(wl["n"], pitch_offset=wl["pitch"], layout_mode=wl["layout"])
     names, R = pkg.rotation_stack(views, wl["active"])
     V = len(names)
-    ex = pkg.Extractor(H, W, d, wl["fov"], R, wl["mode"], device=local_rank, max_batch=8, path=args.path)
+    ex = pkg.Extractor(H, W, d, wl["fov"], R, wl["mode"], device=local_rank, max_batch=int(os.environ.get("X360_BENCH_CHUNK", "0")), path=args.path)
 
     # ---- device-resident batch -------------------------------------------------------------
     host_frames = synth_frames(F, H, W)

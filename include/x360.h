@@ -65,7 +65,8 @@ typedef struct x360_params {
     const double *R;          /* [n_views][9] row-major fp64 from get_rotation_matrix (geometry.py:80-119),
                                  built by the caller with the reference's own numpy ops */
     int32_t device;           /* CUDA ordinal */
-    int32_t max_batch;        /* frames per pipelined chunk in x360_extract_host (0 = default 8) */
+    int32_t max_batch;        /* frames per pipelined chunk in x360_extract_host (0 = default 2: small chunks keep both
+                                 PCIe directions busy; the kernel is far from being the bottleneck there) */
     int32_t path;             /* X360_PATH_* */
     int32_t reserved;
 } x360_params;
