@@ -95,10 +95,13 @@ struct TiledCtrl {
 //
 // raw:   `rows` footprint rows of bw = 48 m bytes, dense, so that 4-pixel groups (12 B) tile it without
 //        a seam between rows: group i of the flat sequence starts at delta + 12 i.
-// pairs: group i -> 32 B (records of its 4 pixels) at 32 i + 16 (i >> 2): a 16-B pad after every 16
-//        records makes the transform's STS.128 (lane stride 32 B) conflict-free while 16 consecutive
-//        records stay within 144 B for the gather's LDS.64.  Record x of footprint row r lives at
-//        r * 3 bw + (x >> 4) * 144 + (x & 15) * 8.
+// pairs: the "pair record" of source pixel x is lo = [B(x) B(x+1) G(x) G(x+1)], hi = [R(x) R(x+1)].
+//        Bilinear keeps them in two planes — lo words at 16 i (group i = 4 pixels), hi halfwords at
+//        8 i — so the transform stores are contiguous (conflict-free STS.128 / STS.64) and the gather
+//        is one LDS.32 + one LDS.U16 per record: 32 lanes span <= 128 B of the lo plane and <= 64 B of
+//        the hi plane, which costs ~3.4 wavefronts per warp where 8-byte records (LDS.64) cost ~4.4
+//        (scripts/bank_sim.py planes).  Row r, pixel x: lo at r * 4 bw/3 + 4 x, hi at r * 2 bw/3 + 2 x.
+//        Lanczos4 keeps contiguous 8-byte records (4 LDS.64 per source row), row pitch 8 bw/3.
 constexpr uint32_t kOffCtl = 0;
 constexpr uint32_t kOffTile = 128;
 static_assert(sizeof(TiledCtrl) <= 128, "ctrl block");
@@ -121,11 +124,16 @@ static_assert(tiled_off_gray(32) % 128 == 0 && tiled_off_gray(16) % 128 == 0, "r
 
 // one raw buffer: rows_max x bw_max, rounded up to the TMA destination alignment
 __host__ __device__ inline uint32_t tiled_raw_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * bw_max) + 127u) & ~127u; }
-__host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max) { return ((uint32_t)(rows_max * 3 * bw_max) + 16u + 15u) & ~15u; }
+// bilinear: lo plane 4 B + hi plane 2 B per source pixel (bw / 3 pixels per row); Lanczos4: 8-byte records
+__host__ __device__ inline uint32_t tiled_lo_bytes(int rows_max, int bw_max) { return (uint32_t)(rows_max * (bw_max / 3) * 4); }
+__host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max, bool lanczos)
+{
+    return ((uint32_t)(rows_max * (bw_max / 3) * (lanczos ? 8 : 6)) + 16u + 15u) & ~15u;
+}
 __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th)
 {
     // ctrl | packed tile | map_x | map_y | [gray] | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
-    return (size_t)tiled_off_raw(scores, th) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max) +
+    return (size_t)tiled_off_raw(scores, th) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
            (lanczos ? (size_t)kTW * 32 * 144 : 0);
 }
 
@@ -219,34 +227,36 @@ __device__ __forceinline__ uint32_t combine_pairs(uint2 r0, uint2 r1, uint32_t w
     return __byte_perm(__byte_perm(vb, vg, 0x0062), vr, 0x7610);
 }
 
-// One step down an output column: (X, Y) are the upper / lower pair records of the previous pixel.
-// Mode bits of pixel K in pm: bit 2K = the lower record becomes the upper one and a new lower record is
-// loaded; bit 2K+1 = the upper record is loaded too.  Predicated-off loads cost no shared-memory
-// bandwidth, which is what bounds this kernel.
-template <int K> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y, uint32_t a_upper, uint32_t a_lower, uint32_t pm)
+// One step down an output column: (X, Y) are the upper / lower pair records of the previous pixel
+// (.x = lo word, .y = hi halfword).  Mode bits of pixel K in pm: bit 2K = the lower record becomes the
+// upper one and a new lower record is loaded; bit 2K+1 = the upper record is loaded too.
+// Predicated-off loads cost no shared-memory bandwidth, which is what bounds this kernel.
+template <int K> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y, uint32_t lo_upper, uint32_t lo_lower,
+                                                              uint32_t hi_upper, uint32_t hi_lower, uint32_t pm)
 {
     asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t;\n\t"
-                 "and.b32 t, %6, %7;\n\tsetp.ne.u32 pA, t, 0;\n\t"
-                 "and.b32 t, %6, %8;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                 "and.b32 t, %8, %9;\n\tsetp.ne.u32 pA, t, 0;\n\t"
+                 "and.b32 t, %8, %10;\n\tsetp.ne.u32 pB, t, 0;\n\t"
                  "@pB mov.b32 %0, %2;\n\t@pB mov.b32 %1, %3;\n\t"
-                 "@pB ld.shared.v2.u32 {%2, %3}, [%5];\n\t"
-                 "@pA ld.shared.v2.u32 {%0, %1}, [%4];\n\t}"
+                 "@pB ld.shared.u32 %2, [%5];\n\t@pB ld.shared.u16 %3, [%7];\n\t"         // u16 -> b32 register: zero-extended
+                 "@pA ld.shared.u32 %0, [%4];\n\t@pA ld.shared.u16 %1, [%6];\n\t}"
                  : "+r"(X.x), "+r"(X.y), "+r"(Y.x), "+r"(Y.y)
-                 : "r"(a_upper), "r"(a_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
+                 : "r"(lo_upper), "r"(lo_lower), "r"(hi_upper), "r"(hi_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
 }
 
 // The same walking UP the column (pixel K after pixel K+1): bit 2K = the upper record becomes the
 // lower one and a new upper record is loaded; bit 2K+1 = the lower record is loaded too.
-template <int K> __device__ __forceinline__ void step_records_up(uint2 &X, uint2 &Y, uint32_t a_upper, uint32_t a_lower, uint32_t pm)
+template <int K> __device__ __forceinline__ void step_records_up(uint2 &X, uint2 &Y, uint32_t lo_upper, uint32_t lo_lower,
+                                                                 uint32_t hi_upper, uint32_t hi_lower, uint32_t pm)
 {
     asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t;\n\t"
-                 "and.b32 t, %6, %7;\n\tsetp.ne.u32 pA, t, 0;\n\t"
-                 "and.b32 t, %6, %8;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                 "and.b32 t, %8, %9;\n\tsetp.ne.u32 pA, t, 0;\n\t"
+                 "and.b32 t, %8, %10;\n\tsetp.ne.u32 pB, t, 0;\n\t"
                  "@pB mov.b32 %2, %0;\n\t@pB mov.b32 %3, %1;\n\t"
-                 "@pB ld.shared.v2.u32 {%0, %1}, [%4];\n\t"
-                 "@pA ld.shared.v2.u32 {%2, %3}, [%5];\n\t}"
+                 "@pB ld.shared.u32 %0, [%4];\n\t@pB ld.shared.u16 %1, [%6];\n\t"
+                 "@pA ld.shared.u32 %2, [%5];\n\t@pA ld.shared.u16 %3, [%7];\n\t}"
                  : "+r"(X.x), "+r"(X.y), "+r"(Y.x), "+r"(Y.y)
-                 : "r"(a_upper), "r"(a_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
+                 : "r"(lo_upper), "r"(lo_lower), "r"(hi_upper), "r"(hi_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
 }
 
 // pair-record words of source pixel J of a 4-pixel group from its packed BGR words w[0..3]
@@ -317,6 +327,19 @@ __device__ __forceinline__ uint32_t lanczos_pairs(uint8_t *dsm, uint32_t a0, uin
     return LanczosSampler::finish(ab, ag, ar);
 }
 
+// 12 (+3) raw bytes at `src` -> the lo words (16 B at dst_lo) and hi halfwords (8 B at dst_hi) of one group
+__device__ __forceinline__ void transform_group_planes(const uint8_t *src, uint8_t *dst_lo, uint8_t *dst_hi)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint32_t *>(src + 4 * i);
+    *reinterpret_cast<uint4 *>(dst_lo) = make_uint4(pair_lo<0>(w), pair_lo<1>(w), pair_lo<2>(w), pair_lo<3>(w));
+    // R(j) = byte 3j + 2: [R0 R1 | R1 R2] = bytes 2, 5, 5, 8; [R2 R3 | R3 R4] = bytes 8, 11, 11, 14
+    const uint32_t h0 = __byte_perm(__byte_perm(w[0], w[1], 0x0552), w[2], 0x4210);
+    const uint32_t h1 = __byte_perm(w[2], w[3], 0x6330);
+    *reinterpret_cast<uint2 *>(dst_hi) = make_uint2(h0, h1);
+}
+
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t src_smem, int x, int y, int z)
 {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
@@ -347,7 +370,8 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     constexpr uint32_t kOffRaw = tiled_off_raw(SCORES, TH);
     const uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
     const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
-    const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
+    const uint32_t off_hi = off_pairs + tiled_lo_bytes(a.rows_max, a.bw_max);          // bilinear: hi plane after the lo plane
+    const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max, LZ) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
 
@@ -477,9 +501,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
 
             // ---- 3. per-pixel gather state: staged {upper record, lower record, w0x, w1x}, direct {off, wx, wy} --
             // (Lanczos4: contiguous records, 8 B per source pixel, state {record of tap (0, 0), table row offset})
-            const uint32_t ppitch = LZ ? (bw / 3u) * 8u : 3u * bw;
-            uint32_t pa[kTP + 1], pa2[kTP + 1], pb[kTP + 1], pc[kTP + 1];
-            pa[kTP] = pa2[kTP] = pb[kTP] = pc[kTP] = 0;
+            const uint32_t ppitch = (bw / 3u) * (LZ ? 8u : 4u);                  // Lanczos4 record rows / bilinear lo-plane rows
+            uint32_t pa[kTP + 1], pa2[kTP + 1], ph[kTP + 1], ph2[kTP + 1], pb[kTP + 1], pc[kTP + 1];   // pa/pa2: lo plane, ph/ph2: hi plane
+            pa[kTP] = pa2[kTP] = ph[kTP] = ph2[kTP] = pb[kTP] = pc[kTP] = 0;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 if constexpr (LZ) {
@@ -492,19 +516,21 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         const LanczosSampler::Px d = LanczosSampler::make_px(sxs[k], sys[k], g, nullptr, dummy);
                         pa[k] = d.off; pb[k] = d.info;
                     }
-                    pa2[k] = 0; pc[k] = 0;
+                    pa2[k] = 0; ph[k] = 0; ph2[k] = 0; pc[k] = 0;
                 } else if (staged) {
                     const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
                     const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
-                    pa[k] = dsm_s + off_pairs + ry * ppitch + (rx >> 4) * 144u + (rx & 15u) * 8u;   // shared-window address
+                    pa[k] = dsm_s + off_pairs + ry * ppitch + rx * 4u;                  // shared-window addresses
                     pa2[k] = pa[k] + ppitch;
+                    ph[k] = dsm_s + off_hi + ry * (ppitch >> 1) + rx * 2u;
+                    ph2[k] = ph[k] + (ppitch >> 1);
                     const uint32_t ax0 = 32u - fx, ay0 = (32u - fy) * 64u, ay1 = fy * 64u;
                     pb[k] = min(ay0 * ax0, 65535u) | ((ay0 * fx) << 16);
                     pc[k] = (ay1 * ax0) | ((ay1 * fx) << 16);
                 } else {
                     bool dummy = false;
                     const LinearSampler::Px d = LinearSampler::make_px(sxs[k], sys[k], g, nullptr, dummy);
-                    pa[k] = d.off; pa2[k] = 0; pb[k] = d.wx; pc[k] = d.wy;
+                    pa[k] = d.off; pa2[k] = 0; ph[k] = 0; ph2[k] = 0; pb[k] = d.wx; pc[k] = d.wy;
                 }
             }
 
@@ -527,8 +553,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
             const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
             uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;                 // in raw buffer 0
-            uint32_t tdst0 = off_pairs + 32u * tid + (LZ ? 0u : 16u * (tid >> 2));
-            asm volatile("" : "+r"(tsrc0), "+r"(tdst0));                 // hoisted out of the frame loop for good
+            uint32_t tdst0 = off_pairs + (LZ ? 32u : 16u) * tid;                   // records / lo plane; hi plane: off_hi + 8 i
+            uint32_t thi0 = off_hi + 8u * tid;
+            asm volatile("" : "+r"(tsrc0), "+r"(tdst0), "+r"(thi0));     // hoisted out of the frame loop for good
             const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
             auto issue_box = [&](int f, uint32_t b) {                    // one thread: frame f -> raw buffer b
                 mbar_arrive_expect_tx(&ctl.mbar[b], box_rows * bw);
@@ -547,9 +574,16 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     mbar_wait(&ctl.mbar[rb], (phase >> rb) & 1u);
                     phase ^= 1u << rb;
                     uint32_t src = tsrc0 + rb * raw_bytes, dst = tdst0;
+                    if constexpr (LZ) {
 #pragma unroll 2
-                    for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += (LZ ? 32u : 36u) * kTT)
-                        transform_group(dsm + src, dsm + dst);
+                        for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 32u * kTT)
+                            transform_group(dsm + src, dsm + dst);
+                    } else {
+                        uint32_t dsth = thi0;
+#pragma unroll 2
+                        for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 16u * kTT, dsth += 8u * kTT)
+                            transform_group_planes(dsm + src, dsm + dst, dsm + dsth);
+                    }
                 }
                 // the TMA store of the previous frame must have finished reading the packed tile
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -584,21 +618,23 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     };
-                    step_records<HC - 1>(X, Y, pa[HC - 1], pa2[HC - 1], pm);          // both records (mode 3)
+                    step_records<HC - 1>(X, Y, pa[HC - 1], pa2[HC - 1], ph[HC - 1], ph2[HC - 1], pm);          // both records (mode 3)
                     X2 = X; Y2 = Y;
-                    step_records<HC>(X2, Y2, pa[HC], pa2[HC], pm);
+                    step_records<HC>(X2, Y2, pa[HC], pa2[HC], ph[HC], ph2[HC], pm);
                     emit(HC - 1, X, Y); emit(HC, X2, Y2);
-                    step_records_up<HC - 2>(X, Y, pa[HC - 2], pa2[HC - 2], pm); step_records<HC + 1>(X2, Y2, pa[HC + 1], pa2[HC + 1], pm);
+                    step_records_up<HC - 2>(X, Y, pa[HC - 2], pa2[HC - 2], ph[HC - 2], ph2[HC - 2], pm); step_records<HC + 1>(X2, Y2, pa[HC + 1], pa2[HC + 1], ph[HC + 1], ph2[HC + 1], pm);
                     emit(HC - 2, X, Y); emit(HC + 1, X2, Y2);
                     if constexpr (kTP == 8) {
-                        step_records_up<1>(X, Y, pa[1], pa2[1], pm); step_records<6>(X2, Y2, pa[6], pa2[6], pm);
+                        step_records_up<1>(X, Y, pa[1], pa2[1], ph[1], ph2[1], pm); step_records<6>(X2, Y2, pa[6], pa2[6], ph[6], ph2[6], pm);
                         emit(1, X, Y); emit(6, X2, Y2);
-                        step_records_up<0>(X, Y, pa[0], pa2[0], pm); step_records<7>(X2, Y2, pa[7], pa2[7], pm);
+                        step_records_up<0>(X, Y, pa[0], pa2[0], ph[0], ph2[0], pm); step_records<7>(X2, Y2, pa[7], pa2[7], ph[7], ph2[7], pm);
                         emit(0, X, Y); emit(7, X2, Y2);
                     }
                     if (SCORES && hvalid) {
-                        const uint2 h0 = *reinterpret_cast<const uint2 *>(dsm + (pa[kTP] - dsm_s));
-                        const uint2 h1 = *reinterpret_cast<const uint2 *>(dsm + (pa2[kTP] - dsm_s));
+                        const uint2 h0 = make_uint2(*reinterpret_cast<const uint32_t *>(dsm + (pa[kTP] - dsm_s)),
+                                                    *reinterpret_cast<const uint16_t *>(dsm + (ph[kTP] - dsm_s)));
+                        const uint2 h1 = make_uint2(*reinterpret_cast<const uint32_t *>(dsm + (pa2[kTP] - dsm_s)),
+                                                    *reinterpret_cast<const uint16_t *>(dsm + (ph2[kTP] - dsm_s)));
                         halo_store_t<TH>(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
                     }
                   }

@@ -175,3 +175,31 @@ def rules():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "rules":
     rules()
+
+def planes():
+    """Split planes: lo words [B0 B1 G0 G1] 4 B per source pixel (LDS.32), hi halfwords [R0 R1] 2 B (LDS.U16)."""
+    H, W, d, fov = 2880, 5760, 1600, 90
+    mx, my = host_map(H, W, d, fov, 45.0, 0.0)
+    sx = np.rint(mx * 32).astype(np.int64); sy = np.rint(my * 32).astype(np.int64)
+    ix = sx >> 5; iy = sy >> 5
+    rng = np.random.default_rng(3)
+    tiles = [(int(a), int(b)) for a, b in rng.integers(0, 50, (250, 2))]
+    tot_lo = tot_hi = tot_64 = 0; n = 0
+    for (ty, tx) in tiles:
+        X = ix[ty*32:ty*32+32, tx*32:tx*32+32]; Y = iy[ty*32:ty*32+32, tx*32:tx*32+32]
+        x_org = X.min() & ~3; ymin = Y.min()
+        npx = X.max() - x_org + 1
+        delta = (3 * x_org) % 16
+        bw = -(-(delta + 3 * (npx + 1)) // 48) * 48
+        gpr = bw // 12
+        for r in range(32):
+            rx = X[r] - x_org; ry = Y[r] - ymin + 1           # the lower record (the one loaded per step)
+            tot_lo += wf32(ry * 16 * gpr + rx * 4)
+            tot_hi += wf32(ry * 8 * gpr + rx * 2)
+            tot_64 += wavefronts(ry[:16] * 3 * bw + (rx[:16] >> 4) * 144 + (rx[:16] & 15) * 8) + \
+                      wavefronts(ry[16:] * 3 * bw + (rx[16:] >> 4) * 144 + (rx[16:] & 15) * 8)
+            n += 1
+    print(f"per warp row-load: pair records LDS.64 {tot_64 / n:.2f} wavefronts; planes LDS.32 {tot_lo / n:.2f} + LDS.U16 {tot_hi / n:.2f} = {(tot_lo + tot_hi) / n:.2f}")
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "planes":
+    planes()
