@@ -209,7 +209,7 @@ struct HostUnits {
     std::vector<double> shift;
 };
 
-HostUnits build_units(const double *R, int V, int W, bool share)
+HostUnits build_units(const double *R, int V, int W, bool share, int max_views = kTMaxUnitViews)
 {
     std::vector<std::vector<int>> members;
     std::vector<std::vector<double>> shifts;
@@ -217,7 +217,7 @@ HostUnits build_units(const double *R, int V, int W, bool share)
         bool placed = false;
         for (size_t u = 0; share && u < members.size() && !placed; ++u) {
             double d;
-            if ((int)members[u].size() < kTMaxUnitViews && yaw_delta(R + 9 * members[u][0], R + 9 * v, &d)) {
+            if ((int)members[u].size() < max_views && yaw_delta(R + 9 * members[u][0], R + 9 * v, &d)) {
                 double sh = d / (2.0 * 3.14159265358979323846) * (double)W;
                 if (sh < 0.0) sh += (double)W;
                 if (sh >= (double)W) sh = 0.0;
@@ -323,11 +323,14 @@ struct x360_plan {
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
     unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
     // tiled path
-    int t_bw = 144, t_rows = 40, t_th = 32, n_units = 0;   // staging capacity, tile height (32 or 16)
+    int t_bw = 144, t_rows = 40, t_th = 32;   // staging capacity, tile height (32 or 16)
+    // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
+    // coarsest one that still yields enough work items without cutting the frame batch into chunks
+    int n_units[4] = {0, 0, 0, 0};
     size_t t_smem[2] = {0, 0};           // dynamic shared memory without / with scores
-    TiledUnit *d_units = nullptr;
-    int *d_unit_view = nullptr;
-    double *d_unit_shift = nullptr;
+    TiledUnit *d_units[4] = {};
+    int *d_unit_view[4] = {};
+    double *d_unit_shift[4] = {};
     // pipelined host path
     int chunk = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
@@ -369,12 +372,8 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.sum_lap2 = (long long *)sum_lap2;
     a.R = pl->d_R;
     a.lz_tab = pl->d_lz;
-    a.units = pl->d_units;
-    a.unit_view = pl->d_unit_view;
-    a.unit_shift = pl->d_unit_shift;
     a.counter = pl->d_modes + 3;
     a.tile_modes = pl->d_modes;
-    a.n_units = pl->n_units;
     a.F = n_frames;
     a.V = pl->p.n_views;
     a.rows_max = pl->t_rows;
@@ -385,11 +384,23 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= pl->t_th;
     if (getenv("X360_NO_TMA_STORE") && atoi(getenv("X360_NO_TMA_STORE"))) a.store_ok = 0;
 
-    // frames per chunk: enough work items for the dynamic scheduler to balance the grid, but as many
-    // frames per item as possible (the map of a tile is evaluated once per item)
+    // Work items = units x tiles x frame chunks, enough of them for the dynamic scheduler to balance the
+    // grid.  The map of a tile is evaluated once per item and the per-view setup once per (item, view), so
+    // prefer whole frame batches: split the view units first (8 -> 4 -> 2 -> 1 views), cut the batch into
+    // chunks only if that is still not enough.
     const int cap = plan_grid(pl, scores);
     const long long tiles = (long long)g.tiles_x * a.tiles_y;
-    long long want_chunks = (6LL * cap + pl->n_units * tiles - 1) / (pl->n_units * tiles);
+    const long long want_items = 6LL * cap;
+    int level = 0;
+    while (level < 3 && pl->n_units[level] * tiles < want_items && pl->n_units[level + 1] > pl->n_units[level]) ++level;
+    if (pl->n_units[level] * tiles < want_items && n_frames > 1) level = 0;   // chunking needed anyway: keep the sharing
+    if (const char *e = getenv("X360_UNIT_LEVEL")) level = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : level;
+    const int n_units = pl->n_units[level];
+    a.units = pl->d_units[level];
+    a.unit_view = pl->d_unit_view[level];
+    a.unit_shift = pl->d_unit_shift[level];
+    a.n_units = n_units;
+    long long want_chunks = (want_items + n_units * tiles - 1) / (n_units * tiles);
     if (want_chunks < 1) want_chunks = 1;
     if (want_chunks > n_frames) want_chunks = n_frames;
     int FG = (int)((n_frames + want_chunks - 1) / want_chunks);
@@ -397,7 +408,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     if (FG > n_frames) FG = n_frames;
     a.FG = FG;
     a.n_chunks = (n_frames + FG - 1) / FG;
-    const long long n_items = (long long)pl->n_units * tiles * a.n_chunks;
+    const long long n_items = (long long)n_units * tiles * a.n_chunks;
     if (n_items > 0x7fffffff) return fail(X360_E_INVALID, "too many work items (%lld)", n_items);
     a.n_items = (int)n_items;
 
@@ -539,14 +550,16 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * 4);
     if (e == cudaSuccess && pl->path == X360_PATH_TILED) {
         const bool share = !(getenv("X360_NO_SHARE") && atoi(getenv("X360_NO_SHARE")));
-        const HostUnits h = build_units(params->R, params->n_views, params->src_w, share);
-        pl->n_units = (int)h.units.size();
-        e = cudaMalloc(&pl->d_units, sizeof(TiledUnit) * h.units.size());
-        if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_view, sizeof(int) * h.view.size());
-        if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_shift, sizeof(double) * h.shift.size());
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_units, h.units.data(), sizeof(TiledUnit) * h.units.size(), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_view, h.view.data(), sizeof(int) * h.view.size(), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_shift, h.shift.data(), sizeof(double) * h.shift.size(), cudaMemcpyHostToDevice);
+        for (int lv = 0; lv < 4 && e == cudaSuccess; ++lv) {
+            const HostUnits h = build_units(params->R, params->n_views, params->src_w, share, kTMaxUnitViews >> lv);
+            pl->n_units[lv] = (int)h.units.size();
+            e = cudaMalloc(&pl->d_units[lv], sizeof(TiledUnit) * h.units.size());
+            if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_view[lv], sizeof(int) * h.view.size());
+            if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_shift[lv], sizeof(double) * h.shift.size());
+            if (e == cudaSuccess) e = cudaMemcpy(pl->d_units[lv], h.units.data(), sizeof(TiledUnit) * h.units.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_view[lv], h.view.data(), sizeof(int) * h.view.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_shift[lv], h.shift.data(), sizeof(double) * h.shift.size(), cudaMemcpyHostToDevice);
+        }
     }
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_R, params->R, sizeof(double) * 9 * params->n_views, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && params->interp == X360_INTERP_LANCZOS4) {
@@ -569,9 +582,11 @@ int x360_plan_destroy(x360_plan *pl)
     cudaFree(pl->d_R);
     cudaFree(pl->d_lz);
     cudaFree(pl->d_modes);
-    cudaFree(pl->d_units);
-    cudaFree(pl->d_unit_view);
-    cudaFree(pl->d_unit_shift);
+    for (int lv = 0; lv < 4; ++lv) {
+        cudaFree(pl->d_units[lv]);
+        cudaFree(pl->d_unit_view[lv]);
+        cudaFree(pl->d_unit_shift[lv]);
+    }
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_frames[i]);
         cudaFree(pl->d_views[i]);
