@@ -33,6 +33,7 @@
 // the aligned-word / byte gathers of LinearSampler.
 #pragma once
 #include <climits>
+#include <type_traits>
 #include <cuda.h>
 
 #include "x360_common.cuh"
@@ -231,9 +232,18 @@ __device__ __forceinline__ uint32_t combine_pairs(uint2 r0, uint2 r1, uint32_t w
 // (.x = lo word, .y = hi halfword).  Mode bits of pixel K in pm: bit 2K = the lower record becomes the
 // upper one and a new lower record is loaded; bit 2K+1 = the upper record is loaded too.
 // Predicated-off loads cost no shared-memory bandwidth, which is what bounds this kernel.
-template <int K> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y, uint32_t lo_upper, uint32_t lo_lower,
-                                                              uint32_t hi_upper, uint32_t hi_lower, uint32_t pm)
+template <int K, bool A = true> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y, uint32_t lo_upper, uint32_t lo_lower,
+                                                                            uint32_t hi_upper, uint32_t hi_lower, uint32_t pm)
 {
+    if (!A) {                                            // no lane of the warp reloads the upper record
+        asm volatile("{\n\t.reg .pred pB;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %6, %7;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                     "@pB mov.b32 %0, %2;\n\t@pB mov.b32 %1, %3;\n\t"
+                     "@pB ld.shared.u32 %2, [%4];\n\t@pB ld.shared.u16 %3, [%5];\n\t}"
+                     : "+r"(X.x), "+r"(X.y), "+r"(Y.x), "+r"(Y.y)
+                     : "r"(lo_lower), "r"(hi_lower), "r"(pm), "n"(1u << (2 * K)));
+        return;
+    }
     asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t;\n\t"
                  "and.b32 t, %8, %9;\n\tsetp.ne.u32 pA, t, 0;\n\t"
                  "and.b32 t, %8, %10;\n\tsetp.ne.u32 pB, t, 0;\n\t"
@@ -246,9 +256,18 @@ template <int K> __device__ __forceinline__ void step_records(uint2 &X, uint2 &Y
 
 // The same walking UP the column (pixel K after pixel K+1): bit 2K = the upper record becomes the
 // lower one and a new upper record is loaded; bit 2K+1 = the lower record is loaded too.
-template <int K> __device__ __forceinline__ void step_records_up(uint2 &X, uint2 &Y, uint32_t lo_upper, uint32_t lo_lower,
-                                                                 uint32_t hi_upper, uint32_t hi_lower, uint32_t pm)
+template <int K, bool A = true> __device__ __forceinline__ void step_records_up(uint2 &X, uint2 &Y, uint32_t lo_upper, uint32_t lo_lower,
+                                                                               uint32_t hi_upper, uint32_t hi_lower, uint32_t pm)
 {
+    if (!A) {
+        asm volatile("{\n\t.reg .pred pB;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %6, %7;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                     "@pB mov.b32 %2, %0;\n\t@pB mov.b32 %3, %1;\n\t"
+                     "@pB ld.shared.u32 %0, [%4];\n\t@pB ld.shared.u16 %1, [%5];\n\t}"
+                     : "+r"(X.x), "+r"(X.y), "+r"(Y.x), "+r"(Y.y)
+                     : "r"(lo_upper), "r"(hi_upper), "r"(pm), "n"(1u << (2 * K)));
+        return;
+    }
     asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t;\n\t"
                  "and.b32 t, %8, %9;\n\tsetp.ne.u32 pA, t, 0;\n\t"
                  "and.b32 t, %8, %10;\n\tsetp.ne.u32 pB, t, 0;\n\t"
@@ -368,7 +387,8 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     int *const sy_s = reinterpret_cast<int *>(dsm + tiled_off_sy(TH));
     TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + tiled_off_gray(TH));
     constexpr uint32_t kOffRaw = tiled_off_raw(SCORES, TH);
-    const uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
+    uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
+    asm volatile("" : "+r"(raw_bytes));                                             // keep in a register (cheaper than rematerialising)
     const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
     const uint32_t off_hi = off_pairs + tiled_lo_bytes(a.rows_max, a.bw_max);          // bilinear: hi plane after the lo plane
     const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max, LZ) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
@@ -550,6 +570,10 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 pm |= ((same && adv == 0) ? 0u : ((same && adv == 1) ? 1u : 3u)) << (2 * k);
             }
 
+            // does any lane of this warp ever reload the upper record after its first pixel?  (Never where the
+            // source is not minified along y and the source column is constant: most ring / cube tiles.)
+            const bool any_a = __any_sync(0xffffffffu, ((pm & ~(3u << (2 * (HC - 1)))) & 0xaaaaaaaau) != 0u);
+
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
             const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
             uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;                 // in raw buffer 0
@@ -567,8 +591,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             }
 
             // ---- 4. walk the frame chunk ---------------------------------------------------------
-            const uint8_t *fb = a.frames + (size_t)f_begin * frame_bytes;
-            for (int f = f_begin; f < f_end; ++f, fb += frame_bytes, ++it) {
+            for (int f = f_begin; f < f_end; ++f, ++it) {
                 const uint32_t rb = it & 1u;
                 if (staged) {
                     mbar_wait(&ctl.mbar[rb], (phase >> rb) & 1u);
@@ -618,18 +641,23 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     };
-                    step_records<HC - 1>(X, Y, pa[HC - 1], pa2[HC - 1], ph[HC - 1], ph2[HC - 1], pm);          // both records (mode 3)
-                    X2 = X; Y2 = Y;
-                    step_records<HC>(X2, Y2, pa[HC], pa2[HC], ph[HC], ph2[HC], pm);
-                    emit(HC - 1, X, Y); emit(HC, X2, Y2);
-                    step_records_up<HC - 2>(X, Y, pa[HC - 2], pa2[HC - 2], ph[HC - 2], ph2[HC - 2], pm); step_records<HC + 1>(X2, Y2, pa[HC + 1], pa2[HC + 1], ph[HC + 1], ph2[HC + 1], pm);
-                    emit(HC - 2, X, Y); emit(HC + 1, X2, Y2);
-                    if constexpr (kTP == 8) {
-                        step_records_up<1>(X, Y, pa[1], pa2[1], ph[1], ph2[1], pm); step_records<6>(X2, Y2, pa[6], pa2[6], ph[6], ph2[6], pm);
-                        emit(1, X, Y); emit(6, X2, Y2);
-                        step_records_up<0>(X, Y, pa[0], pa2[0], ph[0], ph2[0], pm); step_records<7>(X2, Y2, pa[7], pa2[7], ph[7], ph2[7], pm);
-                        emit(0, X, Y); emit(7, X2, Y2);
-                    }
+                    auto walk = [&](auto reload) {
+                        constexpr bool A = decltype(reload)::value;
+                        step_records<HC - 1>(X, Y, pa[HC - 1], pa2[HC - 1], ph[HC - 1], ph2[HC - 1], pm);          // both records (mode 3)
+                        X2 = X; Y2 = Y;
+                        step_records<HC, A>(X2, Y2, pa[HC], pa2[HC], ph[HC], ph2[HC], pm);
+                        emit(HC - 1, X, Y); emit(HC, X2, Y2);
+                        step_records_up<HC - 2, A>(X, Y, pa[HC - 2], pa2[HC - 2], ph[HC - 2], ph2[HC - 2], pm);
+                        step_records<HC + 1, A>(X2, Y2, pa[HC + 1], pa2[HC + 1], ph[HC + 1], ph2[HC + 1], pm);
+                        emit(HC - 2, X, Y); emit(HC + 1, X2, Y2);
+                        if constexpr (kTP == 8) {
+                            step_records_up<1, A>(X, Y, pa[1], pa2[1], ph[1], ph2[1], pm); step_records<6, A>(X2, Y2, pa[6], pa2[6], ph[6], ph2[6], pm);
+                            emit(1, X, Y); emit(6, X2, Y2);
+                            step_records_up<0, A>(X, Y, pa[0], pa2[0], ph[0], ph2[0], pm); step_records<7, A>(X2, Y2, pa[7], pa2[7], ph[7], ph2[7], pm);
+                            emit(0, X, Y); emit(7, X2, Y2);
+                        }
+                    };
+                    if (any_a) walk(std::true_type{}); else walk(std::false_type{});
                     if (SCORES && hvalid) {
                         const uint2 h0 = make_uint2(*reinterpret_cast<const uint32_t *>(dsm + (pa[kTP] - dsm_s)),
                                                     *reinterpret_cast<const uint16_t *>(dsm + (ph[kTP] - dsm_s)));
@@ -639,6 +667,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     }
                   }
                 } else {
+                    const uint8_t *fb = a.frames + (size_t)f * frame_bytes;
                     auto direct = [&](int k) -> uint32_t {
                         if constexpr (LZ) {
                             const LanczosSampler::Px d = {pa[k], pb[k]};
