@@ -143,14 +143,18 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // ---- tiled path (x360_tiled.cuh) ---------------------------------------------------------------
 typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 
-tiled_fn pick_tiled(bool scores, bool lanczos, int tp)
+// Tile variants: 32x32 = 4 warps x 8 rows per thread; 32x16 = 4 warps x 4 rows.  (2 warps x 8 rows, 64-thread
+// CTAs, was measured too: equal on cfg2, 20-25 % slower where footprints are large — half the warps per SM.)
+int tiled_warps(bool, int) { return 4; }
+
+tiled_fn pick_tiled(bool scores, bool lanczos, int th)
 {
-    if (tp == 4) {
-        if (lanczos) return scores ? extract_tiled<true, true, 4> : extract_tiled<false, true, 4>;
-        return scores ? extract_tiled<true, false, 4> : extract_tiled<false, false, 4>;
+    if (th == 16) {
+        if (lanczos) return scores ? extract_tiled<true, true, 4, 4> : extract_tiled<false, true, 4, 4>;
+        return scores ? extract_tiled<true, false, 4, 4> : extract_tiled<false, false, 4, 4>;
     }
-    if (lanczos) return scores ? extract_tiled<true, true, 8> : extract_tiled<false, true, 8>;
-    return scores ? extract_tiled<true, false, 8> : extract_tiled<false, false, 8>;
+    if (lanczos) return scores ? extract_tiled<true, true, 8, 4> : extract_tiled<false, true, 8, 4>;
+    return scores ? extract_tiled<true, false, 8, 4> : extract_tiled<false, false, 8, 4>;
 }
 
 // load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W];
@@ -345,7 +349,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th / kTW), kTT, pl->t_smem[scores ? 1 : 0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th), 32 * tiled_warps(scores, pl->t_th), pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -425,7 +429,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th / kTW)<<<grid, kTT, pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
+    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th)<<<grid, 32 * tiled_warps(scores, pl->t_th), pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -516,7 +520,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         pl->t_rows = rows;
         for (int sc = 0; sc < 2; ++sc) {
             pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, params->interp == X360_INTERP_LANCZOS4, th);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, params->interp == X360_INTERP_LANCZOS4, th / kTW), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, params->interp == X360_INTERP_LANCZOS4, th), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];
                 delete pl;
@@ -607,7 +611,7 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (!pl) return fail(X360_E_INVALID, "null plan");
     if (path) *path = pl->path;
     if (grid) *grid = plan_grid(pl, false);
-    if (block) *block = pl->path == X360_PATH_TILED ? kTT : kThreads;
+    if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->t_th) : kThreads;
     if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->t_smem[0]
                                   : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
     return X360_OK;

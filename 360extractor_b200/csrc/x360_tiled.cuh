@@ -43,8 +43,7 @@
 
 namespace x360 {
 
-constexpr int kTT = 128;              // threads per CTA: 4 warps, lanes along x
-constexpr int kTW = kTT / 32;         // warps per CTA; warp w owns tile rows TP w .. TP w + TP - 1
+constexpr int kTWMax = 4;             // warps per CTA: NW = 4 or 2, lanes along x; warp w owns tile rows TP w .. TP w + TP - 1
 // TP = output pixels (rows) per thread: 8 (32x32 tiles) or 4 (32x16 tiles, for geometries whose
 // footprints are too large to keep enough CTAs per SM with 32 rows)
 constexpr int kTBoxRows = 8;          // granularity of the footprint row capacity
@@ -85,9 +84,9 @@ struct TiledArgs {
 };
 
 struct TiledCtrl {
-    int wbb[kTW][4];                  // per-warp footprint bounding boxes (16-B aligned rows)
+    int wbb[kTWMax][4];                  // per-warp footprint bounding boxes (16-B aligned rows)
     unsigned long long mbar[2];       // one per raw buffer
-    int wsum[kTW][2];                 // per-warp (sum L, sum L^2) of the current frame's tile (exact in 32 bits)
+    int wsum[kTWMax][2];                 // per-warp (sum L, sum L^2) of the current frame's tile (exact in 32 bits)
     int item;
 };
 
@@ -135,7 +134,7 @@ __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, boo
 {
     // ctrl | packed tile | map_x | map_y | [gray] | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
     return (size_t)tiled_off_raw(scores, th) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
-           (lanczos ? (size_t)kTW * 32 * 144 : 0);
+           (lanczos ? (size_t)kTWMax * 32 * 144 : 0);
 }
 
 // Halo pixel of thread `tid`: 0-31 top, 32-63 bottom, then TH left, TH right.  False if tid has none.
@@ -366,8 +365,14 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t s
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <bool SCORES, bool LZ, int TP>
-__global__ void __launch_bounds__(kTT, LZ ? (TP == 4 ? 5 : 4) : (TP == 4 ? (SCORES ? 6 : 7) : (SCORES ? 4 : 5)))
+// Occupancy targets (CTAs per SM) the register allocation aims for, by variant.
+__host__ __device__ constexpr int tiled_min_ctas(bool scores, bool lz, int tp, int nw)
+{
+    return nw == 2 ? (lz ? 8 : 10) : (lz ? (tp == 4 ? 5 : 4) : (tp == 4 ? (scores ? 6 : 7) : (scores ? 4 : 5)));
+}
+
+template <bool SCORES, bool LZ, int TP, int NW>
+__global__ void __launch_bounds__(32 * NW, tiled_min_ctas(SCORES, LZ, TP, NW))
 extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
@@ -379,7 +384,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     const size_t opitch = (size_t)g.ow * 3;
 
     static_assert(TP == 8 || TP == 4, "the gather is written out for 8 or 4 rows per thread");
+    static_assert(NW == 4 || (NW == 2 && !SCORES), "the halo of the fused score needs 64 + 2 TH threads");
     constexpr int kTP = TP;
+    constexpr int kTW = NW, kTT = 32 * NW;                                          // warps / threads per CTA
     constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
     uint8_t *const otile = dsm + kOffTile;
@@ -622,7 +629,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 asm volatile("" : "+r"(obase));
                 uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
                 if (staged) {
-                    if (f + 2 < f_end && tid == 32) issue_box(f + 2, rb);          // this frame's raw rows are consumed
+                    if (f + 2 < f_end && tid == kTT - 32) issue_box(f + 2, rb);          // this frame's raw rows are consumed
                   if constexpr (LZ) {
 #pragma unroll
                     for (int k = 0; k < kTP; ++k) {
