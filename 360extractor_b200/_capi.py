@@ -51,7 +51,7 @@ SYMBOLS = {
     "x360_blur_sums": (ctypes.c_int, [_i32, _vp, _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "x360_lanczos4_table": (ctypes.c_int, [_vp]),
     "x360_focal": (_dbl, [_i32, _dbl]),
-    "x360_plan_preview": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(_i32), _vp, _vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
+    "x360_plan_preview": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(_i32), _vp, _vp, _vp, _vp, _vp]),
     "x360_host_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp)]),
     "x360_host_free": (ctypes.c_int, [_vp]),
     "x360_last_error": (ctypes.c_char_p, []),

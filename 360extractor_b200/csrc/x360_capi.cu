@@ -250,15 +250,16 @@ HostUnits build_units(const double *R, int V, int W, bool share, int max_views =
     return h;
 }
 
-// Host estimate of the per-tile source footprints (9 sample points of each tile incl. halo) -> the tile
+// Host estimate of the per-tile source footprints (9 sample points of each tile, + the 1-px halo the fused
+// score gathers when `scores`) -> the tile
 // height (32 or 16 output rows) and staging capacity (footprint rows, raw bytes per row) that maximise
 //   (throughput factor of the CTAs/SM the shared-memory size allows) x (factor of the tile height)
 //   / (cost of the tiles that fit + 3 x the tiles that do not: those go through the direct gathers).
 // Seam-wrapping and pole tiles never fit whatever the capacity.
-void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, int *rows_out, int *bw_out, int *tile_h_out)
+void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, int *rows_out, int *bw_out, int *tile_h_out)
 {
-    // measured on cfg2 (B200): 5 CTAs/SM 1.0, 4 CTAs 0.92; fewer CTAs hide less latency
-    static const double occ_factor[9] = {0.0, 0.35, 0.6, 0.8, 0.92, 1.0, 1.04, 1.06, 1.08};
+    // measured on cfg2 (B200): 4 CTAs/SM 0.92, 5 CTAs 1.0, 6 CTAs 1.10; fewer CTAs hide less latency
+    static const double occ_factor[9] = {0.0, 0.35, 0.6, 0.8, 0.92, 1.0, 1.10, 1.14, 1.17};
     double best = -1.0;
     int best_rows = 40, best_bw = 144, best_th = 32;
     const int m = lanczos ? 7 : 0;                                        // 8x8 taps: 3 before, 4 after
@@ -277,8 +278,9 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, int *r
                     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
                     for (int j = 0; j < 3; ++j)
                         for (int i = 0; i < 3; ++i) {
-                            const double x = std::min<double>(std::max(0, tx * kTile - 1 + i * 33 / 2), g.ow - 1);
-                            const double y = std::min<double>(std::max(0, ty * th - 1 + j * (th + 1) / 2), g.oh - 1);
+                            const int hl = scores ? 1 : 0;                        // halo
+                            const double x = std::min<double>(std::max(0, tx * kTile - hl + i * (kTile - 1 + 2 * hl) / 2), g.ow - 1);
+                            const double y = std::min<double>(std::max(0, ty * th - hl + j * (th - 1 + 2 * hl) / 2), g.oh - 1);
                             const double xn = (x - g.cx) / g.f, yn = (y - g.cy) / g.f;
                             const double v0 = xn * Rv[0] + yn * Rv[1] + Rv[2], v1 = xn * Rv[3] + yn * Rv[4] + Rv[5],
                                          v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
@@ -294,11 +296,11 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, int *r
                     bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);    // worst alignment
                 }
         }
-        // 16-row tiles pay the per-frame overheads over half the pixels and reuse fewer records (cfg2: 0.85)
-        const double th_factor = th == 32 ? 1.0 : 0.85;
+        // 16-row tiles pay the per-frame overheads over half the pixels and reuse fewer records (cfg2: 0.89 at equal CTAs/SM)
+        const double th_factor = th == 32 ? 1.0 : 0.93;
         for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
             for (int r = 24; r <= 96; r += kTBoxRows) {
-                const size_t smem = tiled_smem_bytes(r, bw, false, lanczos, th) + 1024;
+                const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th) + 1024;
                 if (smem > 110 * 1024) continue;
                 int occ = (int)((227 * 1024) / smem);
                 occ = occ > 8 ? 8 : occ;
@@ -327,7 +329,7 @@ struct x360_plan {
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
     unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
     // tiled path
-    int t_bw = 144, t_rows = 40, t_th = 32;   // staging capacity, tile height (32 or 16)
+    int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with scores
     // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
     // coarsest one that still yields enough work items without cutting the frame batch into chunks
     int n_units[4] = {0, 0, 0, 0};
@@ -349,7 +351,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th), 32 * tiled_warps(scores, pl->t_th), pl->t_smem[scores ? 1 : 0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th[scores ? 1 : 0]), 32 * tiled_warps(scores, pl->t_th[scores ? 1 : 0]), pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -380,12 +382,13 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.tile_modes = pl->d_modes;
     a.F = n_frames;
     a.V = pl->p.n_views;
-    a.rows_max = pl->t_rows;
-    a.bw_max = pl->t_bw;
-    a.tiles_y = (g.oh + pl->t_th - 1) / pl->t_th;
+    const int sc = scores ? 1 : 0, t_rows = pl->t_rows[sc], t_th = pl->t_th[sc];
+    a.rows_max = t_rows;
+    a.bw_max = pl->t_bw[sc];
+    a.tiles_y = (g.oh + t_th - 1) / t_th;
     a.aligned = ((uintptr_t)frames % 4 == 0) && (g.W % 4 == 0);
-    a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= pl->t_rows && g.W * 3 >= 256;
-    a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= pl->t_th;
+    a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= t_rows && g.W * 3 >= 256;
+    a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= t_th;
     if (getenv("X360_NO_TMA_STORE") && atoi(getenv("X360_NO_TMA_STORE"))) a.store_ok = 0;
 
     // Work items = units x tiles x frame chunks, enough of them for the dynamic scheduler to balance the
@@ -419,7 +422,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     TiledMaps tms;
     memset(&tms, 0, sizeof tms);
     if ((a.stage_ok || a.store_ok) &&
-        !encode_tiled_maps(frames, n_frames, g.H, g.W, pl->t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, pl->t_th, a.store_ok != 0, &tms)) {
+        !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, t_th, a.store_ok != 0, &tms)) {
         a.stage_ok = 0;                                   // every tile goes direct, byte stores
         a.store_ok = 0;
     }
@@ -429,7 +432,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th)<<<grid, 32 * tiled_warps(scores, pl->t_th), pl->t_smem[scores ? 1 : 0], st>>>(a, tms);
+    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th)<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -466,12 +469,14 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
             if (unit_of_view) unit_of_view[h.view[e]] = (int32_t)u;
             if (shift_px) shift_px[h.view[e]] = h.shift[e];
         }
-    int rows = 0, bw = 0, th = 0;
-    choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
-                    params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw, &th);
-    if (rows_max) *rows_max = rows;
-    if (bw_max) *bw_max = bw;
-    if (tile_h) *tile_h = th;
+    for (int sc = 0; sc < 2; ++sc) {
+        int rows = 0, bw = 0, th = 0;
+        choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
+                        params->n_views, params->interp == X360_INTERP_LANCZOS4, sc != 0, &rows, &bw, &th);
+        if (rows_max) rows_max[sc] = rows;
+        if (bw_max) bw_max[sc] = bw;
+        if (tile_h) tile_h[sc] = th;
+    }
     return X360_OK;
 }
 
@@ -509,18 +514,19 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->path = params->path == X360_PATH_DIRECT ? X360_PATH_DIRECT
                : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
     if (pl->path == X360_PATH_TILED) {
-        // staging capacity from a host survey of the tiles' footprints
-        int rows = 40, bw = 144, th = 32;
-        choose_capacity(pl->g, params->R, params->n_views, params->interp == X360_INTERP_LANCZOS4, &rows, &bw, &th);
-        pl->t_th = th;
-        if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
-        if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-        while (rows > 24 && tiled_smem_bytes(rows, bw, true, params->interp == X360_INTERP_LANCZOS4, th) > 110 * 1024) rows -= kTBoxRows;
-        pl->t_bw = bw;
-        pl->t_rows = rows;
+        // staging capacity and tile height from a host survey of the tiles' footprints, without / with the score halo
+        const bool lz = params->interp == X360_INTERP_LANCZOS4;
         for (int sc = 0; sc < 2; ++sc) {
-            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, params->interp == X360_INTERP_LANCZOS4, th);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, params->interp == X360_INTERP_LANCZOS4, th), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            int rows = 40, bw = 144, th = 32;
+            choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, &rows, &bw, &th);
+            if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
+            if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
+            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th) > 110 * 1024) rows -= kTBoxRows;
+            pl->t_th[sc] = th;
+            pl->t_bw[sc] = bw;
+            pl->t_rows[sc] = rows;
+            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];
                 delete pl;
@@ -611,7 +617,7 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (!pl) return fail(X360_E_INVALID, "null plan");
     if (path) *path = pl->path;
     if (grid) *grid = plan_grid(pl, false);
-    if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->t_th) : kThreads;
+    if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->t_th[0]) : kThreads;
     if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->t_smem[0]
                                   : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
     return X360_OK;

@@ -43,6 +43,9 @@
 
 namespace x360 {
 
+#ifndef X360_MINB8
+#define X360_MINB8 6          // CTAs per SM the 32x32 bilinear variant's register allocation aims for
+#endif
 constexpr int kTWMax = 4;             // warps per CTA: NW = 4 or 2, lanes along x; warp w owns tile rows TP w .. TP w + TP - 1
 // TP = output pixels (rows) per thread: 8 (32x32 tiles) or 4 (32x16 tiles, for geometries whose
 // footprints are too large to keep enough CTAs per SM with 32 rows)
@@ -115,7 +118,7 @@ template <int TH> struct TGray {
 
 __host__ __device__ constexpr uint32_t tiled_off_u0(int th) { return kOffTile + (uint32_t)th * kTile * 3; }
 __host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return tiled_off_u0(th) + (uint32_t)th * kTile * 8; }
-__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 4; }
+__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 3; }   // Q5 map_y: 3 byte planes (< 2^20)
 __host__ __device__ constexpr uint32_t tiled_off_raw(bool scores, int th)
 {
     return scores ? ((tiled_off_gray(th) + (uint32_t)((th + 2) * kTile + 2 * th) + 127u) & ~127u) : tiled_off_gray(th);
@@ -368,7 +371,7 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t s
 // Occupancy targets (CTAs per SM) the register allocation aims for, by variant.
 __host__ __device__ constexpr int tiled_min_ctas(bool scores, bool lz, int tp, int nw)
 {
-    return nw == 2 ? (lz ? 8 : 10) : (lz ? (tp == 4 ? 5 : 4) : (tp == 4 ? (scores ? 6 : 7) : (scores ? 4 : 5)));
+    return nw == 2 ? (lz ? 8 : 10) : (lz ? (tp == 4 ? 5 : 4) : (tp == 4 ? (scores ? 6 : 7) : (scores ? 4 : X360_MINB8)));
 }
 
 template <bool SCORES, bool LZ, int TP, int NW>
@@ -391,7 +394,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
     uint8_t *const otile = dsm + kOffTile;
     double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(TH));
-    int *const sy_s = reinterpret_cast<int *>(dsm + tiled_off_sy(TH));
+    uint8_t *const sy_s = dsm + tiled_off_sy(TH);                                   // 3 byte planes of TH x 32 values
     TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + tiled_off_gray(TH));
     constexpr uint32_t kOffRaw = tiled_off_raw(SCORES, TH);
     uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
@@ -441,7 +444,10 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 double uf; float my;
                 map_f64(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), uf, my);
                 u0s[k * kTT + tid] = uf;
-                sy_s[k * kTT + tid] = q5_of(my);
+                const int syq = q5_of(my);                                 // 0 .. 32 H < 2^20
+                sy_s[k * kTT + tid] = (uint8_t)syq;
+                sy_s[TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 8);
+                sy_s[2 * TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 16);
             }
             if (SCORES) {
                 int hx = -1, hy = -1;
@@ -466,7 +472,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 double uu = u0s[k * kTT + tid] + shift;
                 if (uu > Wd) uu -= Wd;
                 sxs[k] = q5_of(__double2float_rn(uu));
-                sys[k] = sy_s[k * kTT + tid];
+                sys[k] = (int)sy_s[k * kTT + tid] | ((int)sy_s[TH * kTile + k * kTT + tid] << 8) | ((int)sy_s[2 * TH * kTile + k * kTT + tid] << 16);
             }
             sxs[kTP] = sxs[0];
             sys[kTP] = sys[0];

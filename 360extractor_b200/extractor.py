@@ -43,13 +43,15 @@ def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear",
     p.interp = interp_code(interpolation_mode)
     p.n_views = int(R.shape[0])
     p.R = R.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-    n_units, rows, bw, th = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    n_units = ctypes.c_int32()
+    rows, bw, th = (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)()
     unit = np.zeros(p.n_views, np.int32)
     shift = np.zeros(p.n_views, np.float64)
     check(lib().x360_plan_preview(ctypes.byref(p), ctypes.byref(n_units), unit.ctypes.data, shift.ctypes.data,
-                                  ctypes.byref(rows), ctypes.byref(bw), ctypes.byref(th)))
+                                  rows, bw, th))
     return {"n_units": n_units.value, "unit_of_view": unit.tolist(), "shift_px": shift.tolist(),
-            "rows_max": rows.value, "bw_max": bw.value, "tile_h": th.value}
+            "rows_max": rows[0], "bw_max": bw[0], "tile_h": th[0],
+            "with_scores": {"rows_max": rows[1], "bw_max": bw[1], "tile_h": th[1]}}
 
 
 class Extractor:

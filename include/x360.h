@@ -139,10 +139,11 @@ double x360_focal(int32_t out_w, double fov_deg);
  *                 horizontal cube faces: src/core/geometry.py:24-37,71-75), so they share ONE map evaluation
  *   unit_of_view  [n_views] unit index of each view (units are ordered largest first)
  *   shift_px      [n_views] map_x shift of the view relative to its unit's first view, in source pixels [0, W)
- *   rows_max, bw_max  staging capacity chosen from a survey of the tiles' source footprints
+ *   rows_max, bw_max  [2] staging capacity chosen from a survey of the tiles' source footprints
  *                 (footprint rows; raw bytes per footprint row, a multiple of 48)
- *   tile_h        output tile height the plan works in: 32, or 16 where 32-row footprints would leave too
- *                 few CTAs per SM (tiles are 32 pixels wide)
+ *   tile_h        [2] output tile height the plan works in: 32, or 16 where 32-row footprints would leave
+ *                 too few CTAs per SM (tiles are 32 pixels wide)
+ *                 index 0: extraction without scores, index 1: with the fused blur score (1-px halo)
  * Any output pointer may be NULL.
  */
 int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,

@@ -102,7 +102,8 @@ def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
         got_ns, none = ex.extract(frames, want_scores=False)      # the no-score kernel variant
     assert none is None
     if interp == 0 and path in (0, 2):
-        tile_h = x360.plan_preview(H, W, d, fov, R)["tile_h"] if path == 0 else 32     # tiles are 32 wide, 32 or 16 high
+        # tiles are 32 wide, 32 or 16 high; `modes` is of the launch with scores
+        tile_h = x360.plan_preview(H, W, d, fov, R)["with_scores"]["tile_h"] if path == 0 else 32
         assert sum(modes.values()) == len(views) * ((d + 31) // 32) * ((d + tile_h - 1) // tile_h)
         scale = (W / (2 * np.pi)) / ((d / 2) / np.tan(np.radians(fov) / 2))     # source px per output px at the centre
         if W % 16 == 0 and scale < 1.5:                  # footprints too large for a profitable staging capacity go direct
