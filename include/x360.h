@@ -42,9 +42,9 @@ extern "C" {
 /* kernel-path selector (x360_params.path): 0 lets the plan choose */
 #define X360_PATH_AUTO    0
 #define X360_PATH_DIRECT  1   /* taps gathered straight from global/L2 through L1 */
-#define X360_PATH_STAGED  2   /* per-tile source footprint staged in shared memory by bulk async copies */
+#define X360_PATH_STAGED  2   /* the earlier staged bilinear kernel (kept as a comparison path) */
 #define X360_PATH_TILED   3   /* TMA in / pair records / dp2a gather / TMA out, maps shared across yaw-shifted views
-                                 (bilinear; what AUTO resolves to) */
+                                 (bilinear and Lanczos4; what AUTO resolves to) */
 
 typedef struct x360_plan x360_plan;
 
