@@ -1,28 +1,31 @@
-// x360_tiled.cuh — bilinear extraction, the bench kernel: TMA in, pair records, dp2a gather, TMA out.
+// x360_tiled.cuh — the extraction kernel: TMA in, pair records in shared memory, dp2a gather, TMA out.
 //
-// Contract: src/core/processor.py:327-342 for a frame batch (cv2.remap INTER_LINEAR + BORDER_WRAP,
-// optional calculate_blur_score), map of src/core/geometry.py:141-190 evaluated on the fly and
-// never stored in HBM.  Differences from x360_staged.cuh (kept as the comparison path) are about
-// instruction and shared-memory traffic per output pixel, not about arithmetic:
+// Contract: src/core/processor.py:327-342 for a frame batch — cv2.remap(INTER_LINEAR | INTER_LANCZOS4,
+// BORDER_WRAP) and, optionally, calculate_blur_score — with the map of src/core/geometry.py:141-190
+// evaluated on the fly and never stored in HBM.  extract_tiled<SCORES, LZ, TP, NW>:
 //
-//   work item   = (view unit, 32x32 output tile, frame chunk), handed out by a global atomic
-//                 counter.  A view unit is a set of views whose rotations differ only by a yaw
-//                 (ring layouts, the four horizontal cube faces): their maps are one fp64 map plus
-//                 a per-view shift of map_x, so the atan2/asin evaluation is done once per item
-//                 and shared by all views and frames of the item.
-//   per view    : Q5 coordinates from the shared map (+ shift, in fp64 before the float32
-//                 rounding), bounding box of the 2x2 footprints, per-pixel gather state
-//                 (pair-record address, two packed 16-bit weight pairs): 3 registers per pixel.
-//   per frame   : 1. footprint rows arrive in `raw` by TMA boxes (UTMALDG.3D) on an mbarrier;
-//                 2. transform: 8 source pixels per thread, 24 B of packed BGR -> eight 8-byte
-//                    "pair" records [B(x) B(x+1) G(x) G(x+1)] [R(x) R(x+1) . .], stored as four
-//                    conflict-free STS.128 (records are laid out in 4 planes of 16-byte chunks);
-//                 3. gather: per output pixel 2 LDS.64 + 6 dp2a (weights (32-fy|fy)(32-fx|fx)*64
-//                    as u16 pairs, bias 2^15: the result (V + 512) >> 10 lands in byte 2) + 2 PRMT;
-//                 4. pack: one SHFL + one PRMT turn four lanes' pixels into three BGR words,
-//                    STS.32 into the packed tile, which leaves by ONE TMA store (UTMASTG) per
-//                    tile and frame — no per-row address arithmetic, no store instructions in
-//                    the SM's LSU pipe.
+//   work item   = (view unit, 32 x (NW TP) output tile, frame chunk), handed out by a global atomic
+//                 counter.  A view unit is a set of views whose rotations differ only by a yaw (ring
+//                 layouts, the four horizontal cube faces): their maps are one fp64 map plus a per-view
+//                 shift of map_x, so the atan2 evaluations are done once per item and shared by all
+//                 views and frames of the item.
+//   per view    : Q5 coordinates from the shared map (+ shift, in fp64 before the float32 rounding),
+//                 bounding box of the footprints, staging decision, per-pixel gather state.
+//   per frame   : 1. the footprint arrives in one of two `raw` buffers as ONE TMA box (UTMALDG.3D) on
+//                    an mbarrier, two frames ahead;
+//                 2. transform: thread i turns the i-th 4-pixel group of the box (12 B of packed BGR)
+//                    into the "pair records" of its pixels — lo = [B(x) B(x+1) G(x) G(x+1)],
+//                    hi = [R(x) R(x+1)] — bilinear: two planes (STS.128 + STS.64, conflict-free),
+//                    Lanczos4: contiguous 8-byte records;
+//                 3. gather, bilinear: per output pixel the upper and lower record (LDS.32 + LDS.U16
+//                    each), 6 dp2a (weights (32-fy|fy)(32-fx|fx)*64 as u16 pairs, bias 2^15: the
+//                    result (V + 512) >> 10 lands in byte 2) + 2 PRMT; a thread walks its output
+//                    column and keeps the records in registers, so most pixels load ONE record;
+//                    Lanczos4: 8 source rows x 4 LDS.64 x 3 dp2a with cv2's int16 weight pairs, the
+//                    per-pixel weight rows transposed through shared memory;
+//                 4. pack: one SHFL + one PRMT turn four lanes' pixels into three BGR words, STS.32
+//                    into the packed tile, which leaves by ONE TMA store (UTMASTG) per tile and frame;
+//                 5. SCORES: gray tile + 1-px halo, dp4a Laplacian, integer sums (image_utils.py:22-27).
 //
 // Exactness of the u16 weights: w*64 <= 65535 except w00 = 1024 (fx = fy = 0, all other weights
 // 0), which is clamped to 65535: (65535 s + 32768) >> 16 = s for every byte s.  Everything else
@@ -30,7 +33,7 @@
 //
 // Tiles whose footprint wraps the seam, touches a pole, exceeds the staging capacity or whose
 // geometry defeats the TMA alignment rules fall back per (tile, view), inside the same launch, to
-// the aligned-word / byte gathers of LinearSampler.
+// the aligned-word / byte gathers of LinearSampler / LanczosSampler.
 #pragma once
 #include <climits>
 #include <type_traits>
