@@ -9,6 +9,7 @@ The directory name starts with a digit, so import it with
 ``importlib.import_module("360extractor_b200")`` or through the ``x360`` alias at the repo root.
 """
 from ._capi import INTERP_LANCZOS4, INTERP_LINEAR, X360Error, launch_count, version
+from .analyzer import BlurAnalyzer
 from .blur_filter import BlurFilter
 from .extractor import Extractor, PinnedBuffer, plan_preview, remap, scores_from_sums
 from .geometry import GeometryProcessor, focal_length, rotation_stack
@@ -19,7 +20,7 @@ from .sharding import gather_sums, shard_bounds, shard_sizes
 __version__ = "0.1.0"
 
 __all__ = [
-    "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter",
+    "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "BlurAnalyzer",
     "PinnedBuffer", "plan_preview", "remap", "scores_from_sums", "rotation_stack", "focal_length",
     "gather_sums", "shard_bounds", "shard_sizes",
     "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",

@@ -231,6 +231,24 @@ def test_session_mirrors_processor_loop(x360, oracle):
         assert k.image.flags.c_contiguous and k.image.flags.writeable
 
 
+def test_blur_analyzer_mirrors_reference(x360, oracle):
+    """BlurAnalyzer.analyze_frame = src/core/analyzer.py:44-76: ring layout whatever layout_mode says,
+    bilinear, resolution default 1024; scores from the fused kernel == the oracle's to 1e-12."""
+    frame = smooth_frame(5, 256, 512)
+    settings = {"resolution": 96, "fov": 100, "camera_count": 5, "pitch_offset": -20, "layout_mode": "cube",
+                "interpolation_mode": "lanczos"}
+    res = x360.BlurAnalyzer.analyze_frame(frame, settings)
+    views = x360.GeometryProcessor.generate_views(5, pitch_offset=-20)           # ring
+    _, R = x360.rotation_stack(views)
+    _, s, s2 = oracle.extract(frame[None], R, 96, 100, 0)
+    want = [oracle.score_from_sums(s[0, v], s2[0, v], 96 * 96) for v in range(5)]
+    assert [n for n, _ in res["details"]] == [v[0] for v in views]
+    np.testing.assert_allclose([sc for _, sc in res["details"]], want, rtol=SCORE_RTOL)
+    assert res["average"] == pytest.approx(sum(want) / 5, rel=SCORE_RTOL)
+    assert res["min"] == pytest.approx(min(want), rel=SCORE_RTOL) and res["max"] == pytest.approx(max(want), rel=SCORE_RTOL)
+    assert all(isinstance(sc, float) for _, sc in res["details"])
+
+
 # ---- BASELINE.json configurations at full size ------------------------------------------------
 FULL = [
     # name, (H, W), layout, n, pitch, active, d, fov, mode, F, views to check against the oracle
