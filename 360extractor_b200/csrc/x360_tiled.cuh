@@ -371,6 +371,23 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *tm, uint32_t s
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// mbarrier / TMA helpers on 32-bit shared-window addresses kept in registers (the pointer forms make the
+// compiler rebuild the window base per use)
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "W_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra W_%=;\n\t}"
+                 ::"r"(bar_s), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_issue_box_s(uint32_t dst_s, const CUtensorMap *tm, int x, int y, int z, uint32_t bar_s, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst_s), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar_s) : "memory");
+}
+
 // Occupancy targets (CTAs per SM) the register allocation aims for, by variant.
 __host__ __device__ constexpr int tiled_min_ctas(bool scores, bool lz, int tp, int nw)
 {
@@ -407,6 +424,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max, LZ) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
+    const uint32_t mbar_s = dsm_s + kOffCtl + (uint32_t)offsetof(TiledCtrl, mbar);
 
     if (tid == 0) { mbar_init(&ctl.mbar[0], 1); mbar_init(&ctl.mbar[1], 1); }
     uint32_t phase = 0;               // bit b: parity of raw buffer b's mbarrier
@@ -592,14 +610,15 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
 
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
             const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
+            int tn = tgroups > tid ? (tgroups - tid + kTT - 1) / kTT : 0;        // this thread's groups per frame
+            asm volatile("" : "+r"(tn));
             uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;                 // in raw buffer 0
             uint32_t tdst0 = off_pairs + (LZ ? 32u : 16u) * tid;                   // records / lo plane; hi plane: off_hi + 8 i
             uint32_t thi0 = off_hi + 8u * tid;
             asm volatile("" : "+r"(tsrc0), "+r"(tdst0), "+r"(thi0));     // hoisted out of the frame loop for good
             const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
             auto issue_box = [&](int f, uint32_t b) {                    // one thread: frame f -> raw buffer b
-                mbar_arrive_expect_tx(&ctl.mbar[b], box_rows * bw);
-                tma_load_box(raw_s + b * raw_bytes, tm, gx0, y_org, f, &ctl.mbar[b]);
+                tma_issue_box_s(raw_s + b * raw_bytes, tm, gx0, y_org, f, mbar_s + 8u * b, box_rows * bw);
             };
             if (staged && tid == 0) {                                    // two frames in flight
                 issue_box(f_begin, it & 1u);
@@ -610,7 +629,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             for (int f = f_begin; f < f_end; ++f, ++it) {
                 const uint32_t rb = it & 1u;
                 if (staged) {
-                    mbar_wait(&ctl.mbar[rb], (phase >> rb) & 1u);
+                    mbar_wait_s(mbar_s + 8u * rb, (phase >> rb) & 1u);
                     phase ^= 1u << rb;
                     uint32_t src = tsrc0 + rb * raw_bytes, dst = tdst0;
                     if constexpr (LZ) {
@@ -619,9 +638,15 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                             transform_group(dsm + src, dsm + dst);
                     } else {
                         uint32_t dsth = thi0;
-#pragma unroll 2
-                        for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 16u * kTT, dsth += 8u * kTT)
+                        if (tn & 1) {
                             transform_group_planes(dsm + src, dsm + dst, dsm + dsth);
+                            src += 12u * kTT; dst += 16u * kTT; dsth += 8u * kTT;
+                        }
+#pragma unroll 1
+                        for (int n = tn >> 1; n > 0; --n, src += 24u * kTT, dst += 32u * kTT, dsth += 16u * kTT) {
+                            transform_group_planes(dsm + src, dsm + dst, dsm + dsth);
+                            transform_group_planes(dsm + src + 12u * kTT, dsm + dst + 16u * kTT, dsm + dsth + 8u * kTT);
+                        }
                     }
                 }
                 // the TMA store of the previous frame must have finished reading the packed tile

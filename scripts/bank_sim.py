@@ -203,3 +203,34 @@ def planes():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "planes":
     planes()
+
+def twin():
+    """Twin-copy raw gather: the footprint is staged twice (byte shifts 0 and 2) so that every pixel pair's 6 bytes
+    lie in two aligned words of one copy; no transform.  Wavefronts of the two LDS.32 per record."""
+    H, W, d, fov = 2880, 5760, 1600, 90
+    mx, my = host_map(H, W, d, fov, 45.0, 0.0)
+    sx = np.rint(mx * 32).astype(np.int64); sy = np.rint(my * 32).astype(np.int64)
+    ix = sx >> 5; iy = sy >> 5
+    rng = np.random.default_rng(3)
+    tiles = [(int(a), int(b)) for a, b in rng.integers(0, 50, (250, 2))]
+    for gran in (16, 32, 64, 128):
+        for cs_off in (0, 16, 32, 64):
+            tot = 0; n = 0; nbytes = 0
+            for (ty, tx) in tiles:
+                X = ix[ty*32:ty*32+32, tx*32:tx*32+32]; Y = iy[ty*32:ty*32+32, tx*32:tx*32+32]
+                x_org = X.min(); ymin = Y.min(); rows = Y.max() - ymin + 2
+                gx0 = (3 * x_org) & ~15; delta = 3 * x_org - gx0
+                need = delta + 3 * (X.max() - x_org + 2) + 2
+                bw = -(-need // gran) * gran
+                CS = -(-(rows * bw) // 128) * 128 + cs_off
+                nbytes += 2 * rows * bw
+                for r in range(32):
+                    p = delta + 3 * (X[r] - x_org)
+                    copy = (p & 3) >> 1
+                    q = p + 2 * copy
+                    a = copy * CS + (Y[r] - ymin + 1) * bw + (q & ~3)
+                    tot += wf32(a) + wf32(a + 4); n += 1
+            print(f"twin gran {gran:3d} copy offset {cs_off:3d}: {tot / n:.2f} wavefronts per record (2 LDS.32); TMA bytes/tile {nbytes / len(tiles):.0f}")
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "twin":
+    twin()
