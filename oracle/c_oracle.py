@@ -50,6 +50,12 @@ def lib() -> ctypes.CDLL:
         L.orc_blur_sums.restype = None
         L.orc_blur_sums.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p, c_i64p]
         L.orc_score_from_sums.restype = ctypes.c_double
+        L.orc_unsharp.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_u8p]
+        L.orc_unsharp.restype = None
+        L.orc_add_weighted.argtypes = [c_u8p, c_u8p, ctypes.c_size_t, ctypes.c_double, c_u8p]
+        L.orc_add_weighted.restype = None
+        L.orc_gauss13_taps.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_int)]
+        L.orc_gauss13_taps.restype = None
         L.orc_score_from_sums.argtypes = [ctypes.c_int64] * 3
         L.orc_extract.restype = None
         L.orc_extract.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f64p,
@@ -133,3 +139,28 @@ def extract(frames, R, d, fov_deg, interp=INTERP_LINEAR, want_scores=True):
     if not want_scores:
         return out, None, None
     return out, s, s2
+
+
+def gauss13_taps(sigma=2.0):
+    """The 13 fixed-point taps (sum 256) of cv2.GaussianBlur(img, (0, 0), sigma) on uint8."""
+    t = (ctypes.c_int * 13)()
+    lib().orc_gauss13_taps(float(sigma), t)
+    return list(t)
+
+
+def unsharp(img, strength):
+    """processor.py:379-381 on one uint8 image [h][w] or [h][w][ch]."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    lib().orc_unsharp(_p(img, ctypes.c_uint8), img.shape[0], img.shape[1], ch, float(strength), _p(out, ctypes.c_uint8))
+    return out
+
+
+def add_weighted(a, g, strength):
+    """cv2.addWeighted(a, 1 + s, g, -s, 0) on uint8 arrays of equal shape."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    g = np.ascontiguousarray(g, dtype=np.uint8)
+    out = np.empty_like(a)
+    lib().orc_add_weighted(_p(a, ctypes.c_uint8), _p(g, ctypes.c_uint8), a.size, float(strength), _p(out, ctypes.c_uint8))
+    return out

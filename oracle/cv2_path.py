@@ -123,3 +123,10 @@ def extract(frames, views, maps, interpolation_mode="linear", want_scores=False,
         outs.append(row)
         scores.append(srow)
     return outs, (np.array(scores, dtype=np.float64) if want_scores else None)
+
+
+def unsharp(image, strength):
+    """src/core/processor.py:379-381 verbatim (also src/ui/preview_widget.py:118-120)."""
+    import cv2
+    gaussian = cv2.GaussianBlur(image, (0, 0), 2.0)
+    return cv2.addWeighted(image, 1.0 + strength, gaussian, -strength, 0)

@@ -12,6 +12,8 @@
  *                             borderMode=cv2.BORDER_WRAP  (interp select :199-200)
  *   orc_remap_lanczos4        same call with cv2.INTER_LANCZOS4
  *   orc_blur_sums             src/utils/image_utils.py:6-27 (calculate_blur_score)
+ *   orc_gauss13_taps, orc_unsharp   src/core/processor.py:379-381 (= src/ui/preview_widget.py:118-120):
+ *                             cv2.GaussianBlur(img, (0, 0), 2.0) + cv2.addWeighted(img, 1 + s, blur, -s, 0)
  *
  * The pixel arithmetic itself lives in a third-party dependency that is NOT
  * under /root/reference: opencv-python (requirements.txt:2 ">=4.8.0", no
@@ -301,4 +303,86 @@ void orc_extract(const uint8_t *frames, int F, int H, int W, const double *R, in
     }
     free(mx);
     free(my);
+}
+
+/* ---- unsharp mask --------------------------------------------------
+ * processor.py:379-381:  gaussian = cv2.GaussianBlur(rect_img, (0, 0), 2.0)
+ *                        rect_img = cv2.addWeighted(rect_img, 1.0 + s, gaussian, -s, 0)
+ * OpenCV's 8-bit GaussianBlur is fixed point (smooth.dispatch.cpp, "GaussianBlurFixedPoint"):
+ *   ksize = cvRound(sigma * 6 + 1) | 1 = 13 for sigma = 2; the double kernel exp(-x^2 / (2 sigma^2)) / sum
+ *   is quantised to 8 fractional bits with error diffusion from the outside in, the centre tap takes
+ *   what is left of 256 (getGaussianKernelFixedPoint_ED) -> {1,2,7,16,31,45,52,45,31,16,7,2,1};
+ *   rows then columns without intermediate rounding, BORDER_REFLECT_101 (repeated for tiny images):
+ *   blur = (sum_j sum_i k_j k_i src + 2^15) >> 16.
+ * addWeighted on uint8 runs in float32: dst = sat_u8(rint(fma(src, f32(1 + s), f32(blur * f32(-s)))))
+ * (round half to even).  Both verified against cv2 4.13.0: 0 differing bytes, every (src, blur) byte
+ * pair x 10 strengths, images from 1x1 to 1023x1023 (tests/golden/make_golden.py, tests/test_oracle.py). */
+void orc_gauss13_taps(double sigma, int *taps /* [13] */)
+{
+    const int n = 13;
+    double k[13], sum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double x = i - (n - 1) * 0.5;
+        k[i] = exp(-0.5 / (sigma * sigma) * x * x);
+        sum += k[i];
+    }
+    double err = 0.0;
+    int acc = 0;
+    for (int i = 0; i < n / 2; ++i) {
+        const double adj = k[i] / sum * 256.0 + err;
+        const int v = (int)nearbyint(adj);
+        err = adj - v;
+        taps[i] = taps[n - 1 - i] = v;
+        acc += 2 * v;
+    }
+    taps[n / 2] = 256 - acc;
+}
+
+static inline int orc_reflect101_any(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+/* cv2.addWeighted(a, 1 + s, g, -s, 0) on n bytes */
+void orc_add_weighted(const uint8_t *a, const uint8_t *g, size_t n, double strength, uint8_t *out)
+{
+    const float alpha = (float)(1.0 + strength), beta = (float)(-strength);
+    for (size_t i = 0; i < n; ++i) {
+        const float t = (float)g[i] * beta;                        /* rounded to float32 */
+        const float q = nearbyintf(fmaf((float)a[i], alpha, t));   /* half to even */
+        out[i] = (uint8_t)(q < 0.f ? 0 : (q > 255.f ? 255 : (int)q));
+    }
+}
+
+/* img, out: uint8 [h][w][ch] (out != img) */
+void orc_unsharp(const uint8_t *img, int h, int w, int ch, double strength, uint8_t *out)
+{
+    int k[13];
+    orc_gauss13_taps(2.0, k);
+    const float alpha = (float)(1.0 + strength), beta = (float)(-strength);
+    const size_t pitch = (size_t)w * ch;
+    int32_t *H = (int32_t *)malloc(sizeof(int32_t) * (size_t)h * pitch);
+    int *xi = (int *)malloc(sizeof(int) * (size_t)w * 13), *yi = (int *)malloc(sizeof(int) * (size_t)h * 13);
+    for (int x = 0; x < w; ++x) for (int i = 0; i < 13; ++i) xi[x * 13 + i] = orc_reflect101_any(x + i - 6, w);
+    for (int y = 0; y < h; ++y) for (int j = 0; j < 13; ++j) yi[y * 13 + j] = orc_reflect101_any(y + j - 6, h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < ch; ++c) {
+                int32_t a = 0;
+                for (int i = 0; i < 13; ++i) a += k[i] * img[y * pitch + (size_t)xi[x * 13 + i] * ch + c];
+                H[y * pitch + (size_t)x * ch + c] = a;
+            }
+    for (int y = 0; y < h; ++y)
+        for (size_t b = 0; b < pitch; ++b) {
+            int32_t v = 0;
+            for (int j = 0; j < 13; ++j) v += k[j] * H[(size_t)yi[y * 13 + j] * pitch + b];
+            const int g = (v + 32768) >> 16;
+            const float t = (float)g * beta;                       /* rounded to float32 */
+            const float r = fmaf((float)img[y * pitch + b], alpha, t);
+            const float q = nearbyintf(r);                         /* half to even */
+            out[y * pitch + b] = (uint8_t)(q < 0.f ? 0 : (q > 255.f ? 255 : (int)q));
+        }
+    free(H); free(xi); free(yi);
 }

@@ -124,7 +124,58 @@ def blur_fixture():
     return out
 
 
+UNSHARP_CASES = [  # (name, shape, strength, kind)
+    ("noise_64", (64, 64, 3), 0.5, "noise"), ("noise_37x53", (37, 53, 3), 0.3, "noise"),
+    ("noise_5x5", (5, 5, 3), 1.7, "noise"), ("noise_1x20", (1, 20, 3), 0.5, "noise"),
+    ("noise_20x1", (20, 1, 3), 0.9, "noise"), ("smooth_100x96", (100, 96, 3), 0.5, "smooth"),
+    ("smooth_48x64", (48, 64, 3), 2.0, "smooth"), ("smooth_96x160", (96, 160, 3), 0.1, "smooth"),
+    ("noise_70x80", (70, 80, 3), 1.3, "noise"), ("smooth_33x47", (33, 47, 3), 0.05, "smooth"),
+]
+
+
+def unsharp_image(k, shape, kind):
+    """Seeded input of case k: uint8 noise, or the same generator at 1/8 size upsampled with INTER_CUBIC."""
+    rng = np.random.default_rng(4000 + k)
+    if kind == "noise":
+        return rng.integers(0, 256, shape, dtype=np.uint8)
+    small = rng.integers(0, 256, (max(2, shape[0] // 8), max(2, shape[1] // 8), shape[2]), dtype=np.uint8)
+    return cv2.resize(small, (shape[1], shape[0]), interpolation=cv2.INTER_CUBIC)
+
+
+def ref_unsharp(img, s):
+    gaussian = cv2.GaussianBlur(img, (0, 0), 2.0)                      # processor.py:380
+    return cv2.addWeighted(img, 1.0 + s, gaussian, -s, 0)              # processor.py:381
+
+
+def unsharp_fixture():
+    """processor.py:379-381 on seeded images; inputs and outputs are committed (small), plus the blur alone
+    and the full byte-pair table of addWeighted for ten strengths (hashes)."""
+    arrays, meta = {}, []
+    for k, (name, shape, s, kind) in enumerate(UNSHARP_CASES):
+        img = unsharp_image(k, shape, kind)
+        arrays[f"in{k}"] = img
+        arrays[f"blur{k}"] = cv2.GaussianBlur(img, (0, 0), 2.0)
+        arrays[f"out{k}"] = ref_unsharp(img, s)
+        meta.append({"name": name, "shape": list(shape), "strength": float(s).hex(), "kind": kind})
+    a, g = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    a, g = np.ascontiguousarray(a), np.ascontiguousarray(g)
+    table = {}
+    for s in (0.5, 0.1, 0.3, 1.0, 2.0, 0.7, 1.3, 0.05, 1.9, 0.25):
+        table[float(s).hex()] = sha(cv2.addWeighted(a, 1.0 + s, g, -s, 0))
+    impulse = np.zeros((25, 25), np.uint8)
+    impulse[12, :] = 255                                               # a row of 255s: the blur's column = round(255 k_j)
+    col = cv2.GaussianBlur(impulse, (0, 0), 2.0)[6:19, 12]
+    return arrays, {"cases": meta, "add_weighted_table_sha": table, "line_response": [int(v) for v in col]}
+
+
 def main():
+    if "--only-unsharp" in sys.argv:
+        arrays, meta = unsharp_fixture()
+        np.savez_compressed(os.path.join(HERE, "unsharp_cases.npz"), **arrays)
+        with open(os.path.join(HERE, "unsharp.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+        print("unsharp fixtures written")
+        return
     with open(os.path.join(HERE, "geometry.json"), "w") as f:
         json.dump(geometry_fixture(), f, indent=1)
     with open(os.path.join(HERE, "kat_512x1024.json"), "w") as f:
@@ -135,6 +186,10 @@ def main():
         json.dump(meta, f, indent=1)
     with open(os.path.join(HERE, "blur.json"), "w") as f:
         json.dump(blur_fixture(), f, indent=1)
+    arrays, meta = unsharp_fixture()
+    np.savez_compressed(os.path.join(HERE, "unsharp_cases.npz"), **arrays)
+    with open(os.path.join(HERE, "unsharp.json"), "w") as f:
+        json.dump(meta, f, indent=1)
     info = {"cv2": cv2.__version__, "numpy": np.__version__, "reference": REF,
             "threads": cv2.getNumThreads()}
     with open(os.path.join(HERE, "PROVENANCE.json"), "w") as f:

@@ -1,6 +1,7 @@
 """The oracle against the committed golden fixtures (generated from the REAL reference by
 tests/golden/make_golden.py).  CPU only."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -114,3 +115,28 @@ def test_cv2_path_matches_c_oracle(oracle):
             got = oracle.remap(src, mx, my, interp)
             assert np.array_equal(got, outs[0][j])
             assert oracle.blur_score(got) == pytest.approx(scores[0, j], rel=1e-12)
+
+
+# ---- unsharp mask (processor.py:379-381): GaussianBlur(sigma 2) + addWeighted ------------------------------
+
+def test_oracle_gauss_taps_and_add_weighted_table(oracle):
+    u = load_json("unsharp.json")
+    taps = oracle.gauss13_taps(2.0)
+    assert taps == [1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1] and sum(taps) == 256
+    assert taps == u["line_response"]          # cv2's response to a line of 255s is the taps themselves
+    a, g = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for s_hex, want in u["add_weighted_table_sha"].items():
+        assert sha(oracle.add_weighted(a, g, unhex(s_hex))) == want, f"strength {unhex(s_hex)}"
+
+
+def test_oracle_unsharp_bit_exact_on_golden(oracle):
+    u = load_json("unsharp.json")
+    z = np.load(os.path.join(GOLDEN, "unsharp_cases.npz"))
+    for k, m in enumerate(u["cases"]):
+        img = z[f"in{k}"]
+        assert list(img.shape) == m["shape"]
+        s = unhex(m["strength"])
+        assert np.array_equal(oracle.unsharp(img, 0.0), img), "strength 0 is the identity"
+        # blur alone: addWeighted(img, 0, blur, 1) == blur  <=>  strength -1
+        assert np.array_equal(oracle.unsharp(img, -1.0), z[f"blur{k}"]), m["name"]
+        assert np.array_equal(oracle.unsharp(img, s), z[f"out{k}"]), m["name"]
