@@ -16,12 +16,13 @@ from .geometry import GeometryProcessor, focal_length, rotation_stack
 from .image_utils import ImageUtils
 from .pipeline import ExtractionSession, ViewResult
 from .sharding import gather_sums, shard_bounds, shard_sizes
+from .sharpen import unsharp_mask, unsharp_mask_device
 
 __version__ = "0.1.0"
 
 __all__ = [
     "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "BlurAnalyzer",
-    "PinnedBuffer", "plan_preview", "remap", "scores_from_sums", "rotation_stack", "focal_length",
+    "PinnedBuffer", "plan_preview", "remap", "unsharp_mask", "unsharp_mask_device", "scores_from_sums", "rotation_stack", "focal_length",
     "gather_sums", "shard_bounds", "shard_sizes",
     "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",
 ]

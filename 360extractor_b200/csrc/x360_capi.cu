@@ -25,6 +25,7 @@
 #include "x360_staged.cuh"
 #include "x360_tables.hpp"
 #include "x360_tiled.cuh"
+#include "x360_unsharp.cuh"
 
 using namespace x360;
 
@@ -851,6 +852,95 @@ int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, i
     *sum_lap = hs[0];
     *sum_lap2 = hs[1];
     return X360_OK;
+}
+
+// ---- unsharp mask: processor.py:379-381 --------------------------------------------------------------
+static int unsharp_launch(const uint8_t *d_in, long long n, int h, int w, double strength, uint8_t *d_out, cudaStream_t st)
+{
+    const float alpha = (float)(1.0 + strength), beta = (float)(-strength);       // addWeighted casts its scalars to float
+    const size_t pitch = (size_t)w * 3;
+    bool tiled = (pitch % 16 == 0) && pitch >= (size_t)kUsBoxW && h >= kUsRows && ((uintptr_t)d_in % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
+    if (const char *e = getenv("X360_UNSHARP_GENERIC")) tiled = tiled && !atoi(e);
+    UnsharpMaps tms;
+    memset(&tms, 0, sizeof tms);
+    if (tiled) {
+        encode_tiled_fn enc = tensor_map_encoder();
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)n};
+        const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * h};
+        const cuuint32_t box_in[3] = {(cuuint32_t)kUsBoxW, (cuuint32_t)kUsRows, 1}, box_out[3] = {(cuuint32_t)(kUsTW * 3), (cuuint32_t)kUsTH, 1};
+        tiled = enc &&
+                enc(&tms.in, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_in, dims, strides, box_in, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                enc(&tms.out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_out, dims, strides, box_out, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (tiled) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(unsharp_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUsSmem));
+            attr_set = true;
+        }
+        for (long long n0 = 0; n0 < n; n0 += 65535) {
+            const dim3 grid((unsigned)((w + kUsTW - 1) / kUsTW), (unsigned)((h + kUsTH - 1) / kUsTH), (unsigned)std::min<long long>(65535, n - n0));
+            unsharp_tiled<<<grid, kUsThreads, kUsSmem, st>>>(tms, h, w, (int)n0, alpha, beta);
+            g_launches.fetch_add(1);
+        }
+    } else {
+        const size_t img = (size_t)h * pitch;
+        for (long long n0 = 0; n0 < n; n0 += 65535) {
+            const dim3 grid((unsigned)((img + 255) / 256), (unsigned)std::min<long long>(65535, n - n0));
+            unsharp_generic<<<grid, 256, 0, st>>>(d_in + (size_t)n0 * img, d_out + (size_t)n0 * img, h, w, alpha, beta);
+            g_launches.fetch_add(1);
+        }
+    }
+    CU(cudaGetLastError());
+    return X360_OK;
+}
+
+static int unsharp_check(int32_t device, const void *in, int64_t n, int32_t h, int32_t w, double strength, const void *out)
+{
+    if (!in || !out) return fail(X360_E_INVALID, "null argument");
+    if (in == out) return fail(X360_E_INVALID, "unsharp cannot run in place (every output needs a 13 x 13 input window)");
+    if (n < 0 || h < 1 || w < 1 || h > 65535 || w > 65535) return fail(X360_E_INVALID, "bad image batch %lld x %d x %d", (long long)n, h, w);
+    if (!(strength == strength) || std::fabs(strength) > 1e6) return fail(X360_E_INVALID, "bad strength %g", strength);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(X360_E_INVALID, "device %d out of range [0, %d)", device, n_dev);
+    CU(cudaSetDevice(device));
+    return X360_OK;
+}
+
+int x360_unsharp_device(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w, double strength,
+                        uint8_t *out, void *cuda_stream)
+{
+    if (int rc = unsharp_check(device, images, n_images, h, w, strength, out)) return rc;
+    if (n_images == 0) return X360_OK;
+    return unsharp_launch(images, n_images, h, w, strength, out, (cudaStream_t)cuda_stream);
+}
+
+int x360_unsharp_host(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w, double strength, uint8_t *out)
+{
+    if (int rc = unsharp_check(device, images, n_images, h, w, strength, out)) return rc;
+    if (n_images == 0) return X360_OK;
+    const size_t img = (size_t)h * w * 3;
+    long long chunk = (long long)std::max<size_t>(1, ((size_t)512 << 20) / img);       // <= 512 MB per device buffer
+    if (chunk > n_images) chunk = n_images;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, img * chunk);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, img * chunk);
+    int rc = X360_OK;
+    for (long long n0 = 0; e == cudaSuccess && rc == X360_OK && n0 < n_images; n0 += chunk) {
+        const long long m = std::min(chunk, (long long)n_images - n0);
+        e = cudaMemcpy(d_in, images + (size_t)n0 * img, img * m, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) rc = unsharp_launch(d_in, m, h, w, strength, d_out, nullptr);
+        if (e == cudaSuccess && rc == X360_OK) e = cudaMemcpy(out + (size_t)n0 * img, d_out, img * m, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(X360_E_CUDA, "unsharp failed: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 int x360_host_alloc(size_t bytes, void **out_ptr)

@@ -6,6 +6,7 @@ Covers exactly the slices of src/core/processor.py that sit on the path:
   :245-265                  views + one "map" per active camera        -> one libx360 plan
   :327-342                  per frame, per view: remap (+ blur score)  -> one batched GPU call
   :341-376                  blur accept/reject, in (frame, view) order -> ``BlurFilter`` replay
+  :228-229,379-381          unsharp mask on the accepted views           -> one batched GPU call (``sharpen.py``)
 Decode, sharpening, AI masking, naming and saving stay with the caller (out of scope).
 """
 from __future__ import annotations
@@ -16,6 +17,7 @@ from typing import List, Optional
 import numpy as np
 
 from .blur_filter import BlurFilter
+from .sharpen import unsharp_mask
 from .extractor import Extractor
 from .geometry import GeometryProcessor, rotation_stack
 from .sharding import gather_sums, shard_bounds
@@ -43,6 +45,9 @@ class ExtractionSession:
             layout_mode = "ring"
         self.interpolation_mode = settings.get("interpolation_mode", "linear")
         self.blur = BlurFilter.from_settings(settings)
+        self.sharpen_enabled = settings.get("sharpening_enabled", False)   # processor.py:228
+        self.sharpen_strength = settings.get("sharpening_strength", 0.5)   # processor.py:229
+        self.device = int(device)
         self.views = GeometryProcessor.generate_views(camera_count, pitch_offset=pitch_offset, layout_mode=layout_mode)
         self.active_cameras = settings.get("active_cameras", None)      # job.py:12
         self.names, R = rotation_stack(self.views, self.active_cameras)
@@ -79,6 +84,9 @@ class ExtractionSession:
                 score = float(scores[f, v]) if scores is not None else None
                 if self.blur.accept(score):
                     kept.append(ViewResult(f, name, views[f, v], score))
+        if self.sharpen_enabled and kept:                               # processor.py:379-381, accepted views only
+            sharp = unsharp_mask(np.stack([k.image for k in kept]), self.sharpen_strength, device=self.device)
+            kept = [ViewResult(k.frame_index, k.camera, sharp[i], k.score) for i, k in enumerate(kept)]
         return kept
 
     def process_sharded(self, frames, rank: int, world_size: int, group=None):

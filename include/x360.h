@@ -149,6 +149,20 @@ double x360_focal(int32_t out_w, double fov_deg);
 int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,
                       int32_t *rows_max, int32_t *bw_max, int32_t *tile_h);
 
+/*
+ * Unsharp mask on a batch of views, the step after the blur filter:
+ *   gaussian = cv2.GaussianBlur(rect_img, (0, 0), 2.0)
+ *   rect_img = cv2.addWeighted(rect_img, 1.0 + strength, gaussian, -strength, 0)
+ * (src/core/processor.py:379-381, src/ui/preview_widget.py:118-120; strength = settings
+ * 'sharpening_strength', processor.py:229).  images / out: uint8 [n_images][h][w][3], out != images.
+ * Bit-exact with OpenCV's fixed-point 13-tap Gaussian (BORDER_REFLECT_101) and its float32 addWeighted.
+ * _device: DEVICE pointers, asynchronous on cuda_stream.  _host: HOST pointers, synchronous.
+ */
+int x360_unsharp_device(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w,
+                        double strength, uint8_t *out, void *cuda_stream);
+int x360_unsharp_host(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w,
+                      double strength, uint8_t *out);
+
 /* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
 int x360_host_alloc(size_t bytes, void **out_ptr);
 int x360_host_free(void *ptr);

@@ -3,6 +3,7 @@ golden fixtures.  Bit-exact for both interpolations (north_star allows 1 LSB for
 tolerance used here is 0), blur scores from exact integer sums (checked to 1e-12 relative against
 the reference's fp64 values; north_star's bound is 1e-4)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -283,3 +284,66 @@ def test_full_size_configs(x360, oracle, cfg):
         assert_same(got[f, v], want[0, 0], f"{name} frame {f} view {names[v]}", LANCZOS_TOL_LSB if interp else 0)
         assert s[f, v] == ws[0, 0] and s2[f, v] == ws2[0, 0]
         assert oracle.blur_sums(got[f, v]) == (s[f, v], s2[f, v])
+
+
+# ---- unsharp mask (processor.py:379-381) ------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_unsharp_matches_golden_and_oracle(x360, oracle):
+    """Committed cv2 outputs (tests/golden/make_golden.py) and the C oracle, bit-exact; the golden cases are small,
+    so they run on the any-size kernel, the seeded larger ones on the TMA-tiled kernel (both are checked)."""
+    u = load_json("unsharp.json")
+    z = np.load(os.path.join(GOLDEN, "unsharp_cases.npz"))
+    for k, m in enumerate(u["cases"]):
+        img, s = z[f"in{k}"], unhex(m["strength"])
+        assert np.array_equal(x360.unsharp_mask(img, s), z[f"out{k}"]), m["name"]
+        assert np.array_equal(x360.unsharp_mask(img, -1.0), z[f"blur{k}"]), m["name"] + " (blur alone)"
+        assert np.array_equal(x360.unsharp_mask(img, 0.0), img)
+    rng = np.random.default_rng(77)
+    for (n, h, w), s in [((3, 96, 96), 0.5), ((2, 44, 112), 1.3), ((1, 130, 208), 0.3), ((2, 97, 128), 2.0), ((1, 45, 96), 0.05),
+                         ((1, 64, 100), 0.5), ((2, 7, 96), 0.7)]:
+        imgs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        imgs[0, : h // 2] //= 3                                    # a darker band: fewer saturated outputs
+        got = x360.unsharp_mask(imgs, s)
+        want = np.stack([oracle.unsharp(im, s) for im in imgs])
+        assert np.array_equal(got, want), f"{(n, h, w)} strength {s}: {(got != want).sum()} bytes differ"
+
+
+@pytest.mark.gpu
+def test_unsharp_paths_agree_at_full_size(x360, oracle, monkeypatch):
+    """1600 x 1600 views (cfg2's size): tiled kernel == any-size kernel == oracle on one view; device entry == host entry."""
+    import torch
+    rng = np.random.default_rng(5)
+    small = rng.integers(0, 256, (2, 200, 200, 3), dtype=np.uint8)
+    imgs = np.ascontiguousarray(np.repeat(np.repeat(small, 8, axis=1), 8, axis=2))
+    imgs[:, ::3, 1::2] ^= 0x55                                     # blocky texture + high-frequency detail
+    tiled = x360.unsharp_mask(imgs, 0.5)
+    assert np.array_equal(tiled[1], oracle.unsharp(imgs[1], 0.5))
+    monkeypatch.setenv("X360_UNSHARP_GENERIC", "1")
+    assert np.array_equal(x360.unsharp_mask(imgs, 0.5), tiled)
+    monkeypatch.delenv("X360_UNSHARP_GENERIC")
+    d_in = torch.from_numpy(imgs).cuda()
+    d_out = torch.empty_like(d_in)
+    x360.unsharp_mask_device(d_in, d_out, 0.5)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), tiled)
+    with pytest.raises(x360.X360Error):
+        x360.unsharp_mask_device(d_in, d_in, 0.5)                  # in place is refused
+
+
+@pytest.mark.gpu
+def test_session_sharpens_accepted_views_only(x360, oracle):
+    """ExtractionSession.process with sharpening_enabled == the reference order: score on the unsharpened view,
+    reject, then sharpen what was kept (processor.py:341-381)."""
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (2, 128, 256, 3), dtype=np.uint8)
+    base = {"resolution": 96, "fov": 90, "camera_count": 4, "layout_mode": "ring", "blur_filter_enabled": True,
+            "blur_threshold": 100.0}
+    with x360.ExtractionSession(dict(base), 128, 256) as plain:
+        ref = plain.process(frames)
+    with x360.ExtractionSession(dict(base, sharpening_enabled=True, sharpening_strength=0.8), 128, 256) as sharp:
+        got = sharp.process(frames)
+    assert [(r.frame_index, r.camera, r.score) for r in got] == [(r.frame_index, r.camera, r.score) for r in ref]
+    assert len(got) > 0
+    for g, r in zip(got, ref):
+        assert np.array_equal(g.image, oracle.unsharp(r.image, 0.8))
