@@ -93,8 +93,9 @@ __device__ __forceinline__ uint32_t us_dp2a_hi(uint32_t a16x2, uint32_t b, uint3
 __device__ __forceinline__ uint32_t us_blend(uint32_t src, uint32_t blur, float alpha, float beta)
 {
     const float t = __fmul_rn((float)blur, beta);
-    const int q = __float2int_rn(__fmaf_rn((float)src, alpha, t));
-    return (uint32_t)min(max(q, 0), 255);
+    uint32_t q;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(__fmaf_rn((float)src, alpha, t)));      // half to even, clamped to 0 .. 255
+    return q;
 }
 
 __global__ void __launch_bounds__(kUsThreads, 5)
@@ -117,25 +118,28 @@ unsharp_tiled(const __grid_constant__ UnsharpMaps tms, int h, int w, int n0, flo
     mbar_wait(bar, 0);
 
     // ---- 2. byte planes: planes[c][r][xp] = pixel (x0 - 6 + xp, y0 - 6 + r), channel c ----------------
+    // (outside the image the box holds zeros; border tiles patch those pixels afterwards)
+    for (int t = tid; t < kUsRows * (kUsPx / 4); t += kUsThreads) {
+        const int r = t / (kUsPx / 4), g = t - r * (kUsPx / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(box + r * kUsBoxW + (kUsLead - 2) + 12 * g);   // bytes 2 .. 13 of 16
+        const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+        const uint32_t b = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);                 // bytes 2, 5, 8, 11
+        const uint32_t g_ = __byte_perm(__byte_perm(w0, w1, 0x0063), __byte_perm(w2, w3, 0x0041), 0x5410);   // 3, 6, 9, 12
+        const uint32_t r_ = __byte_perm(__byte_perm(w1, w2, 0x0630), w3, 0x5210);               // 4, 7, 10, 13
+        uint8_t *dst = planes + r * kUsPlanePitch + 4 * g;
+        *reinterpret_cast<uint32_t *>(dst) = b;
+        *reinterpret_cast<uint32_t *>(dst + kUsRows * kUsPlanePitch) = g_;
+        *reinterpret_cast<uint32_t *>(dst + 2 * kUsRows * kUsPlanePitch) = r_;
+    }
     const bool border = x0 < kUsR || y0 < kUsR || x0 + kUsTW + kUsR > w || y0 + kUsTH + kUsR > h;
-    if (!border) {
-        for (int t = tid; t < kUsRows * (kUsPx / 4); t += kUsThreads) {
-            const int r = t / (kUsPx / 4), g = t - r * (kUsPx / 4);
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(box + r * kUsBoxW + (kUsLead - 2) + 12 * g);   // bytes 2 .. 13 of 16
-            const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
-            const uint32_t b = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);                 // bytes 2, 5, 8, 11
-            const uint32_t g_ = __byte_perm(__byte_perm(w0, w1, 0x0063), __byte_perm(w2, w3, 0x0041), 0x5410);   // 3, 6, 9, 12
-            const uint32_t r_ = __byte_perm(__byte_perm(w1, w2, 0x0630), w3, 0x5210);               // 4, 7, 10, 13
-            uint8_t *dst = planes + r * kUsPlanePitch + 4 * g;
-            *reinterpret_cast<uint32_t *>(dst) = b;
-            *reinterpret_cast<uint32_t *>(dst + kUsRows * kUsPlanePitch) = g_;
-            *reinterpret_cast<uint32_t *>(dst + 2 * kUsRows * kUsPlanePitch) = r_;
-        }
-    } else {
+    if (border) {                                                // uniform over the CTA
+        __syncthreads();
+        // reflect-101: every out-of-image pixel a valid output needs mirrors a pixel inside the box (h, w >= 7 on this path)
         for (int t = tid; t < kUsRows * kUsPx; t += kUsThreads) {
             const int r = t / kUsPx, xp = t - r * kUsPx;
-            const int sy = us_reflect(y0 - kUsR + r, h) - (y0 - kUsR), sx = us_reflect(x0 - kUsR + xp, w) - (x0 - kUsR);
-            // the reflected source lies inside the box for every pixel a valid output needs (h, w >= 7)
+            const int gy = y0 - kUsR + r, gx = x0 - kUsR + xp;
+            if (gy >= 0 && gy < h && gx >= 0 && gx < w) continue;
+            const int sy = us_reflect(gy, h) - (y0 - kUsR), sx = us_reflect(gx, w) - (x0 - kUsR);
             const bool ok = sy >= 0 && sy < kUsRows && sx >= -4 && 3 * sx + kUsLead + 2 < kUsBoxW;
             const uint8_t *src = box + sy * kUsBoxW + kUsLead + 3 * sx;
 #pragma unroll
@@ -144,6 +148,15 @@ unsharp_tiled(const __grid_constant__ UnsharpMaps tms, int h, int w, int n0, flo
     }
     __syncthreads();
 
+    // the 16 row-pass weight words, pinned in registers (as immediates each use costs a uniform move)
+    uint32_t hk[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hk[j][i] = us_hweight(j, i);
+            asm volatile("" : "+r"(hk[j][i]));
+        }
     // ---- 3. rows: hw[c][m][xo] = (H[2m][xo] | H[2m+1][xo] << 16),  H[r][xo] = sum_i k_i planes[c][r][xo + i] ----
     for (int t = tid; t < 3 * (kUsRows / 2) * (kUsTW / 4); t += kUsThreads) {
         const int g = t & 15, cm = t >> 4;                       // cm = c * 22 + m
@@ -159,8 +172,8 @@ unsharp_tiled(const __grid_constant__ UnsharpMaps tms, int h, int w, int n0, flo
             uint32_t s0 = 0, s1 = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                s0 = __dp4a(a[i], us_hweight(j, i), s0);
-                s1 = __dp4a(b[i], us_hweight(j, i), s1);
+                s0 = __dp4a(a[i], hk[j][i], s0);
+                s1 = __dp4a(b[i], hk[j][i], s1);
             }
             o[j] = s0 | (s1 << 16);                              // both <= 255 * 256
         }
@@ -170,6 +183,12 @@ unsharp_tiled(const __grid_constant__ UnsharpMaps tms, int h, int w, int n0, flo
 
     // ---- 4. columns + addWeighted: task (c, 32-pixel segment, 8 output rows) per warp -----------------
     uint8_t *const otile = box;                                  // [32][192]
+    uint32_t vk[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        vk[i] = us_vweight(i);
+        asm volatile("" : "+r"(vk[i]));
+    }
     for (int task = warp; task < 3 * 2 * 4; task += kUsThreads / 32) {
         const int c = task >> 3, seg = (task >> 2) & 1, rb = task & 3;
         const int xo = 32 * seg + lane;
@@ -183,8 +202,8 @@ unsharp_tiled(const __grid_constant__ UnsharpMaps tms, int h, int w, int n0, flo
             uint32_t v0 = 32768u, v1 = 32768u;
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                v0 = us_dp2a_lo(wv[t + i], us_vweight(i), v0);
-                v1 = us_dp2a_hi(wv[t + i], us_vweight(i), v1);
+                v0 = us_dp2a_lo(wv[t + i], vk[i], v0);
+                v1 = us_dp2a_hi(wv[t + i], vk[i], v1);
             }
             const int y = 8 * rb + 2 * t;
             otile[y * (kUsTW * 3) + 3 * xo + c] = (uint8_t)us_blend(ctr[(2 * t) * kUsPlanePitch], v0 >> 16, alpha, beta);
