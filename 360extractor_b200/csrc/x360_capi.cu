@@ -148,8 +148,9 @@ typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 // CTAs, was measured too: equal on cfg2, 20-25 % slower where footprints are large — half the warps per SM.)
 int tiled_warps(bool, int) { return 4; }
 
-tiled_fn pick_tiled(bool scores, bool lanczos, int th)
+tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col = false)
 {
+    if (col && !scores && !lanczos && th == 32) return extract_tiled<false, false, 8, 4, 7>;
     if (th == 16) {
         if (lanczos) return scores ? extract_tiled<true, true, 4, 4> : extract_tiled<false, true, 4, 4>;
         return scores ? extract_tiled<true, false, 4, 4> : extract_tiled<false, false, 4, 4>;
@@ -257,8 +258,22 @@ HostUnits build_units(const double *R, int V, int W, bool share, int max_views =
 //   (throughput factor of the CTAs/SM the shared-memory size allows) x (factor of the tile height)
 //   / (cost of the tiles that fit + 3 x the tiles that do not: those go through the direct gathers).
 // Seam-wrapping and pole tiles never fit whatever the capacity.
+// map_x independent of the output row for every view?  v0 = xn R00 + yn R01 + R02 and v2 = xn R20 + yn R21 + R22 lose
+// yn exactly when R01 = R21 = 0 (yaw-only rotations: ring layouts at pitch 0, the horizontal cube faces).  The one
+// case where the SIGN of a zero product could still matter (v0 = +-0 with v2 < 0: theta = +-pi) is excluded.
+bool column_only_map_x(const double *R, int V)
+{
+    for (int v = 0; v < V; ++v) {
+        const double *r = R + 9 * v;
+        if (r[1] != 0.0 || r[7] != 0.0) return false;
+        if (r[2] == 0.0 && r[8] < 0.0) return false;
+    }
+    return V > 0;
+}
+
 void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, int *rows_out, int *bw_out, int *tile_h_out)
 {
+    const bool col = column_only_map_x(R, V);
     // measured on cfg2 (B200): 4 CTAs/SM 0.92, 5 CTAs 1.0, 6 CTAs 1.10; fewer CTAs hide less latency
     static const double occ_factor[9] = {0.0, 0.35, 0.6, 0.8, 0.92, 1.0, 1.10, 1.14, 1.17};
     double best = -1.0;
@@ -301,7 +316,7 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
         const double th_factor = th == 32 ? 1.0 : 0.93;
         for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
             for (int r = 24; r <= 96; r += kTBoxRows) {
-                const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th) + 1024;
+                const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th, col) + 1024;
                 if (smem > 110 * 1024) continue;
                 int occ = (int)((227 * 1024) / smem);
                 occ = occ > 8 ? 8 : occ;
@@ -330,6 +345,7 @@ struct x360_plan {
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
     unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
     // tiled path
+    bool col_u0 = false;                 // map_x depends on the output column only (yaw-only rotations)
     int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with scores
     // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
     // coarsest one that still yields enough work items without cutting the frame batch into chunks
@@ -352,7 +368,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th[scores ? 1 : 0]), 32 * tiled_warps(scores, pl->t_th[scores ? 1 : 0]), pl->t_smem[scores ? 1 : 0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th[scores ? 1 : 0], pl->col_u0), 32 * tiled_warps(scores, pl->t_th[scores ? 1 : 0]), pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -387,6 +403,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.rows_max = t_rows;
     a.bw_max = pl->t_bw[sc];
     a.tiles_y = (g.oh + t_th - 1) / t_th;
+    a.col_u0 = pl->col_u0 ? 1 : 0;
     a.aligned = ((uintptr_t)frames % 4 == 0) && (g.W % 4 == 0);
     a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= t_rows && g.W * 3 >= 256;
     a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= t_th;
@@ -433,7 +450,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th)<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, tms);
+    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0)<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -517,17 +534,18 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (pl->path == X360_PATH_TILED) {
         // staging capacity and tile height from a host survey of the tiles' footprints, without / with the score halo
         const bool lz = params->interp == X360_INTERP_LANCZOS4;
+        pl->col_u0 = column_only_map_x(params->R, params->n_views) && !(getenv("X360_NO_COL_U0") && atoi(getenv("X360_NO_COL_U0")));
         for (int sc = 0; sc < 2; ++sc) {
             int rows = 40, bw = 144, th = 32;
             choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, &rows, &bw, &th);
             if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
             if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th) > 110 * 1024) rows -= kTBoxRows;
+            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0) > 110 * 1024) rows -= kTBoxRows;
             pl->t_th[sc] = th;
             pl->t_bw[sc] = bw;
             pl->t_rows[sc] = rows;
-            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];
                 delete pl;

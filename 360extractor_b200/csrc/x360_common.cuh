@@ -99,18 +99,32 @@ __device__ __forceinline__ double fast_atan2(double y, double x)
 // numpy is the last ulps of atan2 / asin (asin(v1 / |v|) is evaluated as atan2(v1, hypot(v0, v2))),
 // which the float32 cast + Q5 rounding absorbs except with probability ~1e-10 per pixel
 // ("map exactness").
-__device__ __forceinline__ void map_f64(const double *__restrict__ R, const Geom &g, int x, int y, double &uf, float &my)
+__device__ __forceinline__ void map_ray(const double *__restrict__ R, const Geom &g, int x, int y, double &v0, double &v1, double &v2)
 {
     const double xn = __ddiv_rn((double)x - g.cx, g.f);
     const double yn = __ddiv_rn((double)y - g.cy, g.f);
     // [xn, yn, 1] @ R.T  (geometry.py:164)
-    const double v0 = __dadd_rn(__fma_rn(yn, R[1], __dmul_rn(xn, R[0])), R[2]);
-    const double v1 = __dadd_rn(__fma_rn(yn, R[4], __dmul_rn(xn, R[3])), R[5]);
-    const double v2 = __dadd_rn(__fma_rn(yn, R[7], __dmul_rn(xn, R[6])), R[8]);
-    const double theta = fast_atan2(v0, v2);
+    v0 = __dadd_rn(__fma_rn(yn, R[1], __dmul_rn(xn, R[0])), R[2]);
+    v1 = __dadd_rn(__fma_rn(yn, R[4], __dmul_rn(xn, R[3])), R[5]);
+    v2 = __dadd_rn(__fma_rn(yn, R[7], __dmul_rn(xn, R[6])), R[8]);
+}
+// fp64 map_x before the float32 cast (geometry.py:172,183)
+__device__ __forceinline__ double map_u_of(const Geom &g, double v0, double v2)
+{
+    return __dmul_rn(__dadd_rn(__ddiv_rn(fast_atan2(v0, v2), kTwoPi), 0.5), (double)g.W);
+}
+// float32 map_y (geometry.py:175-176,186,190)
+__device__ __forceinline__ float map_y_of(const Geom &g, double v0, double v1, double v2)
+{
     const double phi = fast_atan2(v1, sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v2, v2))));
-    uf = __dmul_rn(__dadd_rn(__ddiv_rn(theta, kTwoPi), 0.5), (double)g.W);
-    my = __double2float_rn(__dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H));
+    return __double2float_rn(__dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H));
+}
+__device__ __forceinline__ void map_f64(const double *__restrict__ R, const Geom &g, int x, int y, double &uf, float &my)
+{
+    double v0, v1, v2;
+    map_ray(R, g, x, y, v0, v1, v2);
+    uf = map_u_of(g, v0, v2);
+    my = map_y_of(g, v0, v1, v2);
 }
 
 __device__ __forceinline__ void map_f32(const double *__restrict__ R, const Geom &g, int x, int y,

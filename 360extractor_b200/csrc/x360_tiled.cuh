@@ -87,6 +87,7 @@ struct TiledArgs {
     int store_ok;                     // TMA stores possible (out base and pitch 16-B aligned)
     int rows_max, bw_max;             // staging capacity: footprint rows, raw bytes per footprint row (48 k)
     int tiles_y;                      // tile rows per view (tile height 32 or 16)
+    int col_u0;                       // map_x of every view is independent of the output row (R01 = R21 = 0: yaw-only rotations)
 };
 
 struct TiledCtrl {
@@ -97,7 +98,7 @@ struct TiledCtrl {
 };
 
 // Dynamic shared memory, fixed offsets first so every hot address is base + constant:
-//   ctrl | 2 packed BGR tiles | fp64 map_x | Q5 map_y | gray tile | raw (one TMA box) | pair records
+//   ctrl | packed BGR tile | Q5 map_y | gray tile | fp64 map_x (tile or one row) | raw x2 (TMA boxes) | pair records
 //
 // raw:   `rows` footprint rows of bw = 48 m bytes, dense, so that 4-pixel groups (12 B) tile it without
 //        a seam between rows: group i of the flat sequence starts at delta + 12 i.
@@ -119,13 +120,15 @@ template <int TH> struct TGray {
     uint8_t hr[TH];
 };
 
-__host__ __device__ constexpr uint32_t tiled_off_u0(int th) { return kOffTile + (uint32_t)th * kTile * 3; }
-__host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return tiled_off_u0(th) + (uint32_t)th * kTile * 8; }
-__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 3; }   // Q5 map_y: 3 byte planes (< 2^20)
-__host__ __device__ constexpr uint32_t tiled_off_raw(bool scores, int th)
+__host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return kOffTile + (uint32_t)th * kTile * 3; }          // Q5 map_y: 3 byte planes (< 2^20)
+__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 3; }
+// fp64 map_x: a TH x 32 tile, or ONE row of 32 where map_x does not depend on the output row (column-only units)
+__host__ __device__ constexpr uint32_t tiled_off_u0(bool scores, int th)
 {
     return scores ? ((tiled_off_gray(th) + (uint32_t)((th + 2) * kTile + 2 * th) + 127u) & ~127u) : tiled_off_gray(th);
 }
+__host__ __device__ constexpr uint32_t tiled_u0_bytes(int th, bool col_only) { return col_only ? 4u * kTile * 8u : (uint32_t)th * kTile * 8u; }   // column-only: one row per warp
+__host__ __device__ constexpr uint32_t tiled_off_raw(bool scores, int th, bool col_only) { return tiled_off_u0(scores, th) + tiled_u0_bytes(th, col_only); }
 static_assert(tiled_off_gray(32) % 128 == 0 && tiled_off_gray(16) % 128 == 0, "raw buffers must be 128-byte aligned");
 
 // one raw buffer: rows_max x bw_max, rounded up to the TMA destination alignment
@@ -136,10 +139,10 @@ __host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max, 
 {
     return ((uint32_t)(rows_max * (bw_max / 3) * (lanczos ? 8 : 6)) + 16u + 15u) & ~15u;
 }
-__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th)
+__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th, bool col_only)
 {
-    // ctrl | packed tile | map_x | map_y | [gray] | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
-    return (size_t)tiled_off_raw(scores, th) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
+    // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
+    return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
            (lanczos ? (size_t)kTWMax * 32 * 144 : 0);
 }
 
@@ -394,8 +397,10 @@ __host__ __device__ constexpr int tiled_min_ctas(bool scores, bool lz, int tp, i
     return nw == 2 ? (lz ? 8 : 10) : (lz ? (tp == 4 ? 5 : 4) : (tp == 4 ? (scores ? 6 : 7) : (scores ? 4 : X360_MINB8)));
 }
 
-template <bool SCORES, bool LZ, int TP, int NW>
-__global__ void __launch_bounds__(32 * NW, tiled_min_ctas(SCORES, LZ, TP, NW))
+// MINB: the CTAs/SM the register allocation aims for.  The default table, or 7 for 32 x 32 bilinear tiles of
+// yaw-only units: their map_x row leaves 30 KB of shared memory per CTA, and 72 registers then buy a 7th CTA.
+template <bool SCORES, bool LZ, int TP, int NW, int MINB = tiled_min_ctas(SCORES, LZ, TP, NW)>
+__global__ void __launch_bounds__(32 * NW, MINB)
 extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
     extern __shared__ __align__(128) uint8_t dsm[];
@@ -413,10 +418,12 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
     uint8_t *const otile = dsm + kOffTile;
-    double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(TH));
+    double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(SCORES, TH));
     uint8_t *const sy_s = dsm + tiled_off_sy(TH);                                   // 3 byte planes of TH x 32 values
     TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + tiled_off_gray(TH));
-    constexpr uint32_t kOffRaw = tiled_off_raw(SCORES, TH);
+    const bool col_u0 = a.col_u0 != 0;
+    uint32_t kOffRaw = tiled_off_raw(SCORES, TH, col_u0);                           // (a register: two layouts)
+    asm volatile("" : "+r"(kOffRaw));
     uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
     asm volatile("" : "+r"(raw_bytes));                                             // keep in a register (cheaper than rematerialising)
     const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
@@ -462,10 +469,12 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             const int x = min(x0 + lane, g.ow - 1);
 #pragma unroll 1
             for (int k = 0; k < kTP; ++k) {
-                double uf; float my;
-                map_f64(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), uf, my);
-                u0s[k * kTT + tid] = uf;
-                const int syq = q5_of(my);                                 // 0 .. 32 H < 2^20
+                double v0, v1, v2;
+                map_ray(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), v0, v1, v2);
+                // yaw-only rotations: v0 and v2, hence map_x, do not depend on the row: one atan2 per column and warp
+                if (!col_u0) u0s[k * kTT + tid] = map_u_of(g, v0, v2);
+                else if (k == 0) u0s[tid] = map_u_of(g, v0, v2);
+                const int syq = q5_of(map_y_of(g, v0, v1, v2));            // 0 .. 32 H < 2^20
                 sy_s[k * kTT + tid] = (uint8_t)syq;
                 sy_s[TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 8);
                 sy_s[2 * TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 16);
@@ -490,7 +499,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             int sxs[kTP + 1], sys[kTP + 1];
 #pragma unroll
             for (int k = 0; k < kTP; ++k) {
-                double uu = u0s[k * kTT + tid] + shift;
+                double uu = u0s[col_u0 ? tid : k * kTT + tid] + shift;
                 if (uu > Wd) uu -= Wd;
                 sxs[k] = q5_of(__double2float_rn(uu));
                 sys[k] = (int)sy_s[k * kTT + tid] | ((int)sy_s[TH * kTile + k * kTT + tid] << 8) | ((int)sy_s[2 * TH * kTile + k * kTT + tid] << 16);
