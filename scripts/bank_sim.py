@@ -234,3 +234,40 @@ def twin():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "twin":
     twin()
+
+def planes_skew():
+    """Split planes with a per-row skew of c words (lo) / c halfwords (hi): wavefronts of the per-step record load."""
+    H, W, d, fov = 2880, 5760, 1600, 90
+    mx, my = host_map(H, W, d, fov, 45.0, 0.0)
+    sx = np.rint(mx * 32).astype(np.int64); sy = np.rint(my * 32).astype(np.int64)
+    ix = sx >> 5; iy = sy >> 5
+    rng = np.random.default_rng(3)
+    tiles = [(int(a), int(b)) for a, b in rng.integers(0, 50, (250, 2))]
+    res = {}
+    for c in (-3, -2, -1, 0, 1, 2, 3):
+        per_tile = []
+        for (ty, tx) in tiles:
+            X = ix[ty*32:ty*32+32, tx*32:tx*32+32]; Y = iy[ty*32:ty*32+32, tx*32:tx*32+32]
+            x_org = X.min() & ~3; ymin = Y.min()
+            npx = X.max() - x_org + 1
+            delta = (3 * x_org) % 16
+            bw = -(-(delta + 3 * (npx + 1)) // 48) * 48
+            gpr = bw // 12
+            lo = hi = 0
+            for r in range(32):
+                rx = X[r] - x_org; ry = Y[r] - ymin + 1
+                lo += wf32(ry * (16 * gpr + 4 * c) + rx * 4)
+                hi += wf32(ry * (8 * gpr + 2 * c) + rx * 2)
+            slope = np.sign((Y[:, -1] - Y[:, 0]).mean())
+            per_tile.append((lo / 32, hi / 32, slope))
+        res[c] = per_tile
+    for c, v in res.items():
+        print(f"skew {c:+d}: lo {np.mean([a for a, _, _ in v]):.2f} hi {np.mean([b for _, b, _ in v]):.2f}")
+    best = np.mean([min(res[c][i][0] + res[c][i][1] for c in res) for i in range(len(tiles))])
+    print(f"oracle per-tile choice: {best:.2f}")
+    for cp, cn in ((1, -1), (-1, 1), (2, -2), (-2, 2), (1, 0), (0, -1)):
+        tot = np.mean([(res[cp][i][0] + res[cp][i][1]) if res[0][i][2] >= 0 else (res[cn][i][0] + res[cn][i][1]) for i in range(len(tiles))])
+        print(f"rule slope>=0 -> {cp:+d}, else {cn:+d}: {tot:.2f}")
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "planes_skew":
+    planes_skew()
