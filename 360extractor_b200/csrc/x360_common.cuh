@@ -64,6 +64,11 @@ __device__ __forceinline__ int sat_s16(int v) { return max(-32768, min(32767, v)
 // |z| <= tan(pi/8) by folding (mn - mx)/(mn + mx) into the same quotient), an odd polynomial
 // z + z w Q(w), w = z^2 (coefficients from scripts/atan_coeffs.py: Chebyshev fit at 50 digits, max
 // relative error 6.5e-17 in double evaluation), quadrant assembly with hi + lo constants.
+__constant__ double kAtanQ[13] = {
+    -0x1.a71378d0839b7p-7, 0x1.e3ded60e0b4b5p-6, -0x1.4bdeae2516d21p-5, 0x1.816326bd079a1p-5, -0x1.ae847c59c5c84p-5,
+    0x1.e1d20955386eap-5, -0x1.111085dfdddd8p-4, 0x1.3b13aa8a180dbp-4, -0x1.745d170db805ep-4, 0x1.c71c71c5eae8cp-4,
+    -0x1.249249249055bp-3, 0x1.9999999999964p-3, -0x1.5555555555555p-2};
+
 __device__ __forceinline__ double fast_atan2(double y, double x)
 {
     const double ax = fabs(x), ay = fabs(y);
@@ -74,19 +79,9 @@ __device__ __forceinline__ double fast_atan2(double y, double x)
     double z = __ddiv_rn(num, den);
     if (mx == 0.0) z = 0.0;                                          // atan2(+-0, +-0)
     const double w = z * z;
-    double q = -0x1.a71378d0839b7p-7;
-    q = fma(q, w, 0x1.e3ded60e0b4b5p-6);
-    q = fma(q, w, -0x1.4bdeae2516d21p-5);
-    q = fma(q, w, 0x1.816326bd079a1p-5);
-    q = fma(q, w, -0x1.ae847c59c5c84p-5);
-    q = fma(q, w, 0x1.e1d20955386eap-5);
-    q = fma(q, w, -0x1.111085dfdddd8p-4);
-    q = fma(q, w, 0x1.3b13aa8a180dbp-4);
-    q = fma(q, w, -0x1.745d170db805ep-4);
-    q = fma(q, w, 0x1.c71c71c5eae8cp-4);
-    q = fma(q, w, -0x1.249249249055bp-3);
-    q = fma(q, w, 0x1.9999999999964p-3);
-    q = fma(q, w, -0x1.5555555555555p-2);
+    double q = kAtanQ[0];
+#pragma unroll
+    for (int i = 1; i < 13; ++i) q = fma(q, w, kAtanQ[i]);           // constant-bank operands: no register or uniform moves
     double a = fma(z, q * w, z);                                     // atan(z), |z| <= tan(pi/8)
     if (red) a = 0x1.921fb54442d18p-1 + (a + 0x1.1a62633145c07p-55); // pi/4 + atan(z)
     if (ay > ax) a = 0x1.921fb54442d18p+0 - (a - 0x1.1a62633145c07p-54);   // pi/2 - a
