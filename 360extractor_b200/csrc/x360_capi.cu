@@ -358,7 +358,9 @@ struct x360_plan {
     int chunk = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
-    uint8_t *d_frames[2] = {}, *d_views[2] = {};
+    uint8_t *d_frames[2] = {}, *d_views[2] = {}, *d_sharp[2] = {};
+    bool sharpen = false;                // x360_extract_host returns unsharp-masked views (scores stay those of the plain views)
+    double sharpen_strength = 0.5;
     long long *d_sums[2] = {};
     bool pipe_ready = false;
 };
@@ -619,6 +621,7 @@ int x360_plan_destroy(x360_plan *pl)
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_frames[i]);
         cudaFree(pl->d_views[i]);
+        cudaFree(pl->d_sharp[i]);
         cudaFree(pl->d_sums[i]);
         if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
         if (pl->ev_k[i]) cudaEventDestroy(pl->ev_k[i]);
@@ -628,6 +631,15 @@ int x360_plan_destroy(x360_plan *pl)
     if (pl->s_k) cudaStreamDestroy(pl->s_k);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
     delete pl;
+    return X360_OK;
+}
+
+int x360_plan_set_sharpen(x360_plan *pl, int32_t enabled, double strength)
+{
+    if (!pl) return fail(X360_E_INVALID, "null plan");
+    if (!(strength == strength) || std::fabs(strength) > 1e6) return fail(X360_E_INVALID, "bad strength %g", strength);
+    pl->sharpen = enabled != 0;
+    pl->sharpen_strength = strength;
     return X360_OK;
 }
 
@@ -698,8 +710,14 @@ int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, 
     return X360_OK;
 }
 
+static int unsharp_launch(const uint8_t *d_in, long long n, int h, int w, double strength, uint8_t *d_out, cudaStream_t st);
+
 static int pipe_setup(x360_plan *pl)
 {
+    if (pl->pipe_ready && pl->sharpen && !pl->d_sharp[0]) {
+        const size_t vb = (size_t)pl->g.oh * pl->g.ow * 3 * pl->p.n_views;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&pl->d_sharp[i], vb * pl->chunk));
+    }
     if (pl->pipe_ready) return X360_OK;
     const size_t fb = (size_t)pl->g.H * pl->g.W * 3, vb = (size_t)pl->g.oh * pl->g.ow * 3 * pl->p.n_views;
     CU(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
@@ -711,6 +729,7 @@ static int pipe_setup(x360_plan *pl)
         CU(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
         CU(cudaMalloc(&pl->d_frames[i], fb * pl->chunk));
         CU(cudaMalloc(&pl->d_views[i], vb * pl->chunk));
+        if (pl->sharpen) CU(cudaMalloc(&pl->d_sharp[i], vb * pl->chunk));
         CU(cudaMalloc(&pl->d_sums[i], sizeof(long long) * 2 * pl->chunk * pl->p.n_views));
     }
     pl->pipe_ready = true;
@@ -743,10 +762,15 @@ int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, ui
         long long *ds = scores ? pl->d_sums[b] : nullptr;
         long long *ds2 = scores ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
         if (int rc = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return rc;
+        const uint8_t *d_result = pl->d_views[b];
+        if (pl->sharpen) {                          // processor.py:379-381 on the chunk's views, still on the device
+            if (int rc = unsharp_launch(pl->d_views[b], (long long)n * V, pl->g.oh, pl->g.ow, pl->sharpen_strength, pl->d_sharp[b], pl->s_k)) return rc;
+            d_result = pl->d_sharp[b];
+        }
         CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
         // download
         CU(cudaStreamWaitEvent(pl->s_out, pl->ev_k[b], 0));
-        CU(cudaMemcpyAsync(out_views + (size_t)f0 * vb, pl->d_views[b], vb * n, cudaMemcpyDeviceToHost, pl->s_out));
+        CU(cudaMemcpyAsync(out_views + (size_t)f0 * vb, d_result, vb * n, cudaMemcpyDeviceToHost, pl->s_out));
         if (scores) {
             CU(cudaMemcpyAsync(sum_lap + (size_t)f0 * V, ds, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
             CU(cudaMemcpyAsync(sum_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));

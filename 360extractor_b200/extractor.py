@@ -58,7 +58,7 @@ class Extractor:
     """Plan wrapper.  ``R`` is fp64 ``[V][3][3]`` from ``GeometryProcessor.get_rotation_matrix``."""
 
     def __init__(self, src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *,
-                 out_h=None, device=0, max_batch=0, path=_capi.PATH_AUTO):
+                 out_h=None, device=0, max_batch=0, path=_capi.PATH_AUTO, sharpen_strength=None):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
         self.src_h, self.src_w = int(src_h), int(src_w)
         self.out_w = int(out_res)
@@ -81,6 +81,16 @@ class Extractor:
         p.path = int(path)
         self._plan = ctypes.c_void_p()
         check(lib().x360_plan_create(ctypes.byref(p), ctypes.byref(self._plan)))
+        self.sharpen_strength = None
+        if sharpen_strength is not None:
+            self.set_sharpen(sharpen_strength)
+
+    def set_sharpen(self, strength):
+        """``strength`` (float) makes ``extract`` / ``extract_sums`` return unsharp-masked views
+        (src/core/processor.py:379-381, applied on the device before the download); ``None`` turns it off.
+        Scores are always those of the plain views, as in the reference (it filters, then sharpens)."""
+        check(lib().x360_plan_set_sharpen(self._plan, 0 if strength is None else 1, 0.0 if strength is None else float(strength)))
+        self.sharpen_strength = None if strength is None else float(strength)
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):

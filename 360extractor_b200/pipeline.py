@@ -6,7 +6,8 @@ Covers exactly the slices of src/core/processor.py that sit on the path:
   :245-265                  views + one "map" per active camera        -> one libx360 plan
   :327-342                  per frame, per view: remap (+ blur score)  -> one batched GPU call
   :341-376                  blur accept/reject, in (frame, view) order -> ``BlurFilter`` replay
-  :228-229,379-381          unsharp mask on the accepted views           -> one batched GPU call (``sharpen.py``)
+  :228-229,379-381          unsharp mask on the accepted views           -> on the device, inside the batched call
+                                                                          (``Extractor(sharpen_strength=...)``)
 Decode, sharpening, AI masking, naming and saving stay with the caller (out of scope).
 """
 from __future__ import annotations
@@ -17,7 +18,6 @@ from typing import List, Optional
 import numpy as np
 
 from .blur_filter import BlurFilter
-from .sharpen import unsharp_mask
 from .extractor import Extractor
 from .geometry import GeometryProcessor, rotation_stack
 from .sharding import gather_sums, shard_bounds
@@ -54,8 +54,11 @@ class ExtractionSession:
         self.src_h, self.src_w = int(src_h), int(src_w)
         self.extractor = None
         if len(self.names):
+            # sharpening_enabled: every chunk is unsharp-masked on the device between the kernel and the download
+            # (processor.py:379-381); the reference sharpens only the views it keeps, which are the ones returned
             self.extractor = Extractor(src_h, src_w, self.out_res, self.fov, R, self.interpolation_mode,
-                                       device=device, max_batch=max_batch)
+                                       device=device, max_batch=max_batch,
+                                       sharpen_strength=self.sharpen_strength if self.sharpen_enabled else None)
 
     def close(self):
         if self.extractor is not None:
@@ -84,9 +87,6 @@ class ExtractionSession:
                 score = float(scores[f, v]) if scores is not None else None
                 if self.blur.accept(score):
                     kept.append(ViewResult(f, name, views[f, v], score))
-        if self.sharpen_enabled and kept:                               # processor.py:379-381, accepted views only
-            sharp = unsharp_mask(np.stack([k.image for k in kept]), self.sharpen_strength, device=self.device)
-            kept = [ViewResult(k.frame_index, k.camera, sharp[i], k.score) for i, k in enumerate(kept)]
         return kept
 
     def process_sharded(self, frames, rank: int, world_size: int, group=None):

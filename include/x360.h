@@ -158,6 +158,13 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
  * Bit-exact with OpenCV's fixed-point 13-tap Gaussian (BORDER_REFLECT_101) and its float32 addWeighted.
  * _device: DEVICE pointers, asynchronous on cuda_stream.  _host: HOST pointers, synchronous.
  */
+/*
+ * Make x360_extract_host return sharpened views: every chunk is unsharp-masked on the device between the
+ * extraction kernel and the download (no extra trip over PCIe).  The Laplacian sums stay those of the PLAIN
+ * views, as in the reference, which scores and filters before it sharpens (processor.py:341-381).
+ */
+int x360_plan_set_sharpen(x360_plan *plan, int32_t enabled, double strength);
+
 int x360_unsharp_device(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w,
                         double strength, uint8_t *out, void *cuda_stream);
 int x360_unsharp_host(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w,

@@ -347,3 +347,23 @@ def test_session_sharpens_accepted_views_only(x360, oracle):
     assert len(got) > 0
     for g, r in zip(got, ref):
         assert np.array_equal(g.image, oracle.unsharp(r.image, 0.8))
+
+
+@pytest.mark.gpu
+def test_extract_host_with_sharpening_is_extract_then_unsharp(x360, oracle):
+    """Extractor(sharpen_strength=s): the pipelined host path (5 frames in chunks of 2) returns the unsharp-masked views,
+    the sums stay those of the plain views; switching it off restores the plain output."""
+    rng = np.random.default_rng(21)
+    frames = rng.integers(0, 256, (5, 128, 256, 3), dtype=np.uint8)
+    _, R = x360.rotation_stack(x360.GeometryProcessor.generate_views(6, layout_mode="cube"))
+    with x360.Extractor(128, 256, 96, 90, R, "linear", max_batch=2) as ex:
+        plain, s, s2 = ex.extract_sums(frames)
+        ex.set_sharpen(0.6)
+        sharp, t, t2 = ex.extract_sums(frames)
+        ex.set_sharpen(None)
+        again, _ = ex.extract(frames)
+    assert np.array_equal(again, plain)
+    assert np.array_equal(s, t) and np.array_equal(s2, t2)
+    for f in range(5):
+        for v in range(6):
+            assert np.array_equal(sharp[f, v], oracle.unsharp(plain[f, v], 0.6)), (f, v)
