@@ -11,7 +11,7 @@ The directory name starts with a digit, so import it with
 from ._capi import INTERP_LANCZOS4, INTERP_LINEAR, X360Error, launch_count, version
 from .analyzer import BlurAnalyzer
 from .blur_filter import BlurFilter
-from .extractor import Extractor, PinnedBuffer, plan_preview, remap, scores_from_sums
+from .extractor import Extractor, PinnedBuffer, column_only_map_x, plan_preview, remap, scores_from_sums
 from .geometry import GeometryProcessor, focal_length, rotation_stack
 from .image_utils import ImageUtils
 from .pipeline import ExtractionSession, ViewResult
@@ -22,7 +22,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "BlurAnalyzer",
-    "PinnedBuffer", "plan_preview", "remap", "unsharp_mask", "unsharp_mask_device", "scores_from_sums", "rotation_stack", "focal_length",
+    "PinnedBuffer", "column_only_map_x", "plan_preview", "remap", "unsharp_mask", "unsharp_mask_device", "scores_from_sums", "rotation_stack", "focal_length",
     "gather_sums", "shard_bounds", "shard_sizes",
     "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",
 ]

@@ -49,6 +49,7 @@ SYMBOLS = {
     "x360_make_maps": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
     "x360_remap_maps": (ctypes.c_int, [_i32, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "x360_blur_sums": (ctypes.c_int, [_i32, _vp, _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "x360_column_only_map_x": (ctypes.c_int, [_vp, _i32]),
     "x360_plan_set_sharpen": (ctypes.c_int, [_vp, _i32, _dbl]),
     "x360_unsharp_device": (ctypes.c_int, [_i32, _vp, _i64, _i32, _i32, _dbl, _vp, _vp]),
     "x360_unsharp_host": (ctypes.c_int, [_i32, _vp, _i64, _i32, _i32, _dbl, _vp]),

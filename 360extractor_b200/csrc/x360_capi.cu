@@ -634,6 +634,12 @@ int x360_plan_destroy(x360_plan *pl)
     return X360_OK;
 }
 
+int x360_column_only_map_x(const double *R, int32_t n_views)
+{
+    if (!R || n_views < 1) return 0;
+    return column_only_map_x(R, n_views) ? 1 : 0;
+}
+
 int x360_plan_set_sharpen(x360_plan *pl, int32_t enabled, double strength)
 {
     if (!pl) return fail(X360_E_INVALID, "null plan");

@@ -54,6 +54,13 @@ def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear",
             "with_scores": {"rows_max": rows[1], "bw_max": bw[1], "tile_h": th[1]}}
 
 
+def column_only_map_x(R) -> bool:
+    """Host-only: True if ``map_x`` of every view in ``R`` ([V][3][3]) does not depend on the output row (yaw-only
+    rotations) — the plans that take the kernel's one-row ``map_x`` variant."""
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
+    return bool(lib().x360_column_only_map_x(R.ctypes.data, int(R.shape[0])))
+
+
 class Extractor:
     """Plan wrapper.  ``R`` is fp64 ``[V][3][3]`` from ``GeometryProcessor.get_rotation_matrix``."""
 

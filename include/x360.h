@@ -170,6 +170,13 @@ int x360_unsharp_device(int32_t device, const uint8_t *images, int64_t n_images,
 int x360_unsharp_host(int32_t device, const uint8_t *images, int64_t n_images, int32_t h, int32_t w,
                       double strength, uint8_t *out);
 
+/*
+ * Host-only: 1 if map_x of every view (row-major fp64 R[n_views][9], geometry.py:80-119) is independent of the
+ * output row — yaw-only rotations: ring layouts at pitch 0 (geometry.py:71-75), the horizontal cube faces
+ * (geometry.py:30-33).  Such plans keep one fp64 map_x row per warp instead of a tile and run 7 CTAs per SM.
+ */
+int x360_column_only_map_x(const double *R, int32_t n_views);
+
 /* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
 int x360_host_alloc(size_t bytes, void **out_ptr);
 int x360_host_free(void *ptr);

@@ -234,3 +234,22 @@ def test_plan_preview_capacity(x360):
     assert x360.plan_preview(5760, 11520, 2048, 90, x360.rotation_stack(views12, [0, 3, 6, 9])[1])["tile_h"] == 16
     with pytest.raises(x360.X360Error):
         x360.plan_preview(2880, 5760, 1600, 190, x360.rotation_stack(views)[1])
+
+
+def test_column_only_map_x(x360, oracle):
+    """map_x is independent of the output row exactly for yaw-only rotations (R01 = R21 = 0): ring layouts at pitch 0
+    and the horizontal cube faces; any pitch, the Up / Down faces or a roll bring yn back into v0 / v2."""
+    def R_of(layout, n, pitch, active=None):
+        views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout)
+        return x360.rotation_stack(views, active)[1]
+    assert x360.column_only_map_x(R_of("ring", 8, 0))
+    assert x360.column_only_map_x(R_of("ring", 12, 0))
+    assert not x360.column_only_map_x(R_of("ring", 8, -20))
+    assert not x360.column_only_map_x(R_of("cube", 6, 0))
+    assert x360.column_only_map_x(R_of("cube", 6, 0, active=[0, 1, 2, 3]))
+    assert not x360.column_only_map_x(R_of("fibonacci", 8, 0))
+    assert not x360.column_only_map_x(x360.GeometryProcessor.get_rotation_matrix(30.0, 0.0, 5.0)[None])
+    # numerically: for such R the reference map_x has identical rows
+    R = x360.GeometryProcessor.get_rotation_matrix(135.0, 0.0, 0.0)
+    mx, _ = oracle.make_map(180, 360, 48, 48, 90, R)
+    assert x360.column_only_map_x(R[None]) and np.all(mx == mx[0:1])
