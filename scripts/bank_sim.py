@@ -271,3 +271,46 @@ def planes_skew():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "planes_skew":
     planes_skew()
+
+def planes_abs():
+    """Split planes with the row pitch forced to a residue: lo pitch = t (mod 32 words), hi pitch = t (mod 64 halfwords)."""
+    H, W, d, fov = 2880, 5760, 1600, 90
+    mx, my = host_map(H, W, d, fov, 45.0, 0.0)
+    sx = np.rint(mx * 32).astype(np.int64); sy = np.rint(my * 32).astype(np.int64)
+    ix = sx >> 5; iy = sy >> 5
+    rng = np.random.default_rng(3)
+    tiles = [(int(a), int(b)) for a, b in rng.integers(0, 50, (250, 2))]
+    res = {}
+    for t in (None, 0, 1, -1, 2, -2, 3, -3, 4, -4, 8, -8):
+        per_tile = []
+        for (ty, tx) in tiles:
+            X = ix[ty*32:ty*32+32, tx*32:tx*32+32]; Y = iy[ty*32:ty*32+32, tx*32:tx*32+32]
+            x_org = X.min() & ~3; ymin = Y.min()
+            npx = X.max() - x_org + 1
+            delta = (3 * x_org) % 16
+            bw = -(-(delta + 3 * (npx + 1)) // 48) * 48
+            gpr = bw // 12
+            plo, phi = 4 * gpr, 4 * gpr                    # words / halfwords per row
+            if t is not None:
+                plo += (t - plo) % 32
+                phi += (t - phi) % 64
+            lo = hi = 0
+            for r in range(32):
+                rx = X[r] - x_org; ry = Y[r] - ymin + 1
+                lo += wf32((ry * plo + rx) * 4)
+                hi += wf32((ry * phi + rx) * 2)
+            slope = np.sign((Y[:, -1] - Y[:, 0]).mean())
+            per_tile.append((lo / 32, hi / 32, slope))
+        res[t] = per_tile
+        print(f"pitch residue {t}: lo {np.mean([a for a, _, _ in per_tile]):.2f} hi {np.mean([b for _, b, _ in per_tile]):.2f}")
+    for cp, cn in ((1, -1), (-1, 1), (2, -2), (-2, 2), (1, 0), (0, -1)):
+        tot = np.mean([(res[cp][i][0] + res[cp][i][1]) if res[0][i][2] >= 0 else (res[cn][i][0] + res[cn][i][1]) for i in range(len(tiles))])
+        print(f"rule slope>=0 -> {cp:+d}, else {cn:+d}: {tot:.2f}")
+    print("oracle:", np.mean([min(res[t][i][0] + res[t][i][1] for t in res) for i in range(len(tiles))]))
+    for cp, cn in ((1, -1), (2, -2), (4, -4), (8, -8)):
+        lo = np.mean([res[cp][i][0] if res[0][i][2] >= 0 else res[cn][i][0] for i in range(len(tiles))])
+        hi = np.mean([res[cp][i][1] if res[0][i][2] >= 0 else res[cn][i][1] for i in range(len(tiles))])
+        print(f"rule {cp:+d}/{cn:+d}: lo {lo:.2f} hi {hi:.2f}; lo by rule + hi natural: {lo + np.mean([v[1] for v in res[None]]):.2f}")
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "planes_abs":
+    planes_abs()
