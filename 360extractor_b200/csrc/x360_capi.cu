@@ -148,8 +148,17 @@ typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 // CTAs, was measured too: equal on cfg2, 20-25 % slower where footprints are large — half the warps per SM.)
 int tiled_warps(bool, int) { return 4; }
 
+// The raw gather (no transform, x360_tiled.cuh RAW) serves the plans of the 7-CTA variant: bilinear, 32x32 tiles,
+// column-only map_x, no fused score.  X360_NO_RAW=1 keeps them on the pair-record planes.
+bool tiled_raw(bool scores, bool lanczos, int th, bool col)
+{
+    static const bool off = [] { const char *e = getenv("X360_NO_RAW"); return e && atoi(e); }();
+    return col && !scores && !lanczos && th == 32 && !off;
+}
+
 tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col = false)
 {
+    if (tiled_raw(scores, lanczos, th, col)) return extract_tiled<false, false, 8, 4, 7, true>;
     if (col && !scores && !lanczos && th == 32) return extract_tiled<false, false, 8, 4, 7>;
     if (th == 16) {
         if (lanczos) return scores ? extract_tiled<true, true, 4, 4> : extract_tiled<false, true, 4, 4>;
@@ -162,7 +171,7 @@ tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col = false)
 // load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W];
 // store box {96, 32, 1} of uint8 [F*V][oh][3 ow]
 bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max, bool with_in, uint8_t *out, int FV, int oh,
-                       int ow, int tile_h, bool with_out, TiledMaps *tm)
+                       int ow, int tile_h, bool with_out, TiledMaps *tm, bool raw = false)
 {
     encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
@@ -172,7 +181,8 @@ bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max,
         const cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * H};
         for (int k = 0; k < kTNumBox; ++k) {
             const int rows = rows_max - kTBoxRows * (kTNumBoxH - 1 - k / kTNumBoxW);
-            const cuuint32_t box[3] = {(cuuint32_t)(48 * (k % kTNumBoxW + 1)), (cuuint32_t)(rows < 8 ? 8 : rows), 1};
+            const int wk = k % kTNumBoxW;
+            const cuuint32_t box[3] = {(cuuint32_t)(raw ? 64 * (std::min(wk, 3) + 1) : 48 * (wk + 1)), (cuuint32_t)(rows < 8 ? 8 : rows), 1};
             if (enc(&tm->in[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)frames, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -283,6 +293,7 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
     if (const char *e = getenv("X360_TILED_TH")) forced_th = atoi(e);
     for (int th = 32; th >= 16; th -= 16) {
         if (forced_th && forced_th != th) continue;
+        const bool raw = tiled_raw(scores, lanczos, th, col);
         std::vector<int> rows, bws;
         size_t total = 0;
         const int tiles_y = (g.oh + th - 1) / th;
@@ -309,14 +320,15 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
                     if (xmax - xmin > g.W / 2) continue;                  // wraps the seam: never staged
                     rows.push_back(ymax - ymin + 3 + m);
                     const int npx = xmax - (xmin & ~3) + 2 + m;
-                    bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);    // worst alignment
+                    if (raw) bws.push_back((15 + 3 * (xmax - xmin + 3) + 63) / 64 * 64);   // x_org = xmin, worst alignment
+                    else bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);    // worst alignment
                 }
         }
         // 16-row tiles pay the per-frame overheads over half the pixels and reuse fewer records (cfg2: 0.89 at equal CTAs/SM)
         const double th_factor = th == 32 ? 1.0 : 0.93;
-        for (int bw = 96; bw <= 48 * kTNumBoxW; bw += 48)
+        for (int bw = raw ? 128 : 96; bw <= (raw ? 256 : 48 * kTNumBoxW); bw += raw ? 64 : 48)
             for (int r = 24; r <= 96; r += kTBoxRows) {
-                const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th, col) + 1024;
+                const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th, col, raw) + 1024;
                 if (smem > 110 * 1024) continue;
                 int occ = (int)((227 * 1024) / smem);
                 occ = occ > 8 ? 8 : occ;
@@ -442,7 +454,8 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     TiledMaps tms;
     memset(&tms, 0, sizeof tms);
     if ((a.stage_ok || a.store_ok) &&
-        !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, t_th, a.store_ok != 0, &tms)) {
+        !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, t_th, a.store_ok != 0, &tms,
+                           tiled_raw(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0))) {
         a.stage_ok = 0;                                   // every tile goes direct, byte stores
         a.store_ok = 0;
     }
@@ -540,13 +553,17 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         for (int sc = 0; sc < 2; ++sc) {
             int rows = 40, bw = 144, th = 32;
             choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, &rows, &bw, &th);
-            if (const char *e = getenv("X360_TILED_BW")) bw = (atoi(e) >= 48 && atoi(e) <= 48 * kTNumBoxW && atoi(e) % 48 == 0) ? atoi(e) : bw;
+            const bool raw = tiled_raw(sc != 0, lz, th, pl->col_u0);
+            if (const char *e = getenv("X360_TILED_BW")) {
+                const int v = atoi(e), unit = raw ? 64 : 48;
+                bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
+            }
             if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0) > 110 * 1024) rows -= kTBoxRows;
+            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw) > 110 * 1024) rows -= kTBoxRows;
             pl->t_th[sc] = th;
             pl->t_bw[sc] = bw;
             pl->t_rows[sc] = rows;
-            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0);
+            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw);
             const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];

@@ -59,7 +59,7 @@ constexpr int kTNumBox = kTNumBoxW * kTNumBoxH;
 constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
 
 struct TiledMaps {
-    CUtensorMap in[kTNumBox];         // uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]
+    CUtensorMap in[kTNumBox];         // uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]; raw gather: {64 (w + 1), ..}, w < 4
     CUtensorMap out;                  // uint8 [F*V][oh][3 ow], box {96, tile height, 1}
 };
 
@@ -139,8 +139,10 @@ __host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max, 
 {
     return ((uint32_t)(rows_max * (bw_max / 3) * (lanczos ? 8 : 6)) + 16u + 15u) & ~15u;
 }
-__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th, bool col_only)
+__host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th, bool col_only, bool raw = false)
 {
+    // RAW: ctrl | packed tile | map_y | map_x row | raw x2 | second packed tile
+    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3;
     // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
     return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
            (lanczos ? (size_t)kTWMax * 32 * 144 : 0);
@@ -286,6 +288,43 @@ template <int K, bool A = true> __device__ __forceinline__ void step_records_up(
                  : "r"(lo_upper), "r"(lo_lower), "r"(hi_upper), "r"(hi_lower), "r"(pm), "n"(2u << (2 * K)), "n"(1u << (2 * K)));
 }
 
+// RAW variant (no transform): the gather reads the packed BGR bytes of the TMA box directly.  The record of source
+// pixels (x, x+1) is the 6 bytes [B G R B G R] starting at byte a = o & 3 of the aligned word at `addr` (o = byte
+// offset of pixel x in its footprint row): words t0, t1 and, where a = 3, t2.  Two PRMT rebuild the pair record —
+// lo = [B(x) B(x+1) G(x) G(x+1)] from (t0, t1), selector 0x4130 + 0x1111 a; hi = [R(x) R(x+1) . .] from (t1, a = 3 ? t2 : t0),
+// selector bytes (a + 6) & 7, (a + 1) & 7 — so the arithmetic is combine_pairs' as is.  m3 = ~0 where a = 3, else 0.
+// One step of a column walk: bit 2K of pm = P <- Q and Q <- the record at aq; bit 2K+1 = P <- the record at ap.
+// Walking down, P / Q are the upper / lower record; walking up, the lower / upper one.  The words land in the record's
+// own registers; the third word is loaded unpredicated (a register written only under a predicate would be kept
+// alive from frame to frame), then reused under the predicate.
+template <int K, bool A> __device__ __forceinline__ void step_raw(uint2 &P, uint2 &Q, uint32_t ap, uint32_t aq, uint32_t sel_lo,
+                                                                  uint32_t sel_hi, uint32_t pm, uint32_t m3)
+{
+    if (!A) {
+        asm volatile("{\n\t.reg .pred pB;\n\t.reg .b32 t, t2;\n\t"
+                     "and.b32 t, %7, %9;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                     "@pB mov.b32 %0, %2;\n\t@pB mov.b32 %1, %3;\n\t"
+                     "@pB ld.shared.u32 %2, [%4];\n\t@pB ld.shared.u32 %3, [%4+4];\n\tld.shared.u32 t2, [%4+8];\n\t"
+                     "lop3.b32 t2, t2, %2, %8, 0xE4;\n\t"
+                     "@pB prmt.b32 %2, %2, %3, %5;\n\t@pB prmt.b32 %3, %3, t2, %6;\n\t}"
+                     : "+r"(P.x), "+r"(P.y), "+r"(Q.x), "+r"(Q.y)
+                     : "r"(aq), "r"(sel_lo), "r"(sel_hi), "r"(pm), "r"(m3), "n"(1u << (2 * K)));
+        return;
+    }
+    asm volatile("{\n\t.reg .pred pA, pB;\n\t.reg .b32 t, t2;\n\t"
+                 "and.b32 t, %7, %9;\n\tsetp.ne.u32 pB, t, 0;\n\t"
+                 "and.b32 t, %7, %10;\n\tsetp.ne.u32 pA, t, 0;\n\t"
+                 "@pB mov.b32 %0, %2;\n\t@pB mov.b32 %1, %3;\n\t"
+                 "@pB ld.shared.u32 %2, [%4];\n\t@pB ld.shared.u32 %3, [%4+4];\n\tld.shared.u32 t2, [%4+8];\n\t"
+                 "lop3.b32 t2, t2, %2, %8, 0xE4;\n\t"
+                 "@pB prmt.b32 %2, %2, %3, %5;\n\t@pB prmt.b32 %3, %3, t2, %6;\n\t"
+                 "@pA ld.shared.u32 %0, [%11];\n\t@pA ld.shared.u32 %1, [%11+4];\n\t@pA ld.shared.u32 t2, [%11+8];\n\t"
+                 "lop3.b32 t2, t2, %0, %8, 0xE4;\n\t"
+                 "@pA prmt.b32 %0, %0, %1, %5;\n\t@pA prmt.b32 %1, %1, t2, %6;\n\t}"
+                 : "+r"(P.x), "+r"(P.y), "+r"(Q.x), "+r"(Q.y)
+                 : "r"(aq), "r"(sel_lo), "r"(sel_hi), "r"(pm), "r"(m3), "n"(1u << (2 * K)), "n"(2u << (2 * K)), "r"(ap));
+}
+
 // pair-record words of source pixel J of a 4-pixel group from its packed BGR words w[0..3]
 template <int J> __device__ __forceinline__ uint32_t pair_lo(const uint32_t (&w)[4])
 {
@@ -399,10 +438,16 @@ __host__ __device__ constexpr int tiled_min_ctas(bool scores, bool lz, int tp, i
 
 // MINB: the CTAs/SM the register allocation aims for.  The default table, or 7 for 32 x 32 bilinear tiles of
 // yaw-only units: their map_x row leaves 30 KB of shared memory per CTA, and 72 registers then buy a 7th CTA.
-template <bool SCORES, bool LZ, int TP, int NW, int MINB = tiled_min_ctas(SCORES, LZ, TP, NW)>
+//
+// RAW: no transform and no pair-record planes — the gather reads the TMA box itself (step_raw), the footprint rows
+// are 64 k bytes wide, the packed output tile is double-buffered (second copy after the raw buffers) and a frame
+// costs ONE block barrier.  Bilinear, column-only map_x (every pixel of a thread's column has the same byte
+// alignment in its source row, so the two PRMT selectors are per-thread constants), no fused score.
+template <bool SCORES, bool LZ, int TP, int NW, int MINB = tiled_min_ctas(SCORES, LZ, TP, NW), bool RAW = false>
 __global__ void __launch_bounds__(32 * NW, MINB)
 extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
+    static_assert(!RAW || (!LZ && !SCORES), "the raw gather is bilinear without the fused score");
     extern __shared__ __align__(128) uint8_t dsm[];
     const Geom &g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -417,7 +462,6 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     constexpr int kTW = NW, kTT = 32 * NW;                                          // warps / threads per CTA
     constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
-    uint8_t *const otile = dsm + kOffTile;
     double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(SCORES, TH));
     uint8_t *const sy_s = dsm + tiled_off_sy(TH);                                   // 3 byte planes of TH x 32 values
     TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + tiled_off_gray(TH));
@@ -532,13 +576,13 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             // footprint of the taps: bilinear (ix, iy) .. (+1, +1); Lanczos4 (ix-3, iy-3) .. (ix+4, iy+4).
             // Pair records for x in [x_org, xmax + MX1 - 1], source rows [y_org, ymax + MY1].
             constexpr int MX0 = LZ ? 3 : 0, MX1 = LZ ? 4 : 1, MY0 = LZ ? 3 : 0, MY1 = LZ ? 4 : 1;
-            const int x_org = (xmin - MX0) & ~3, y_org = ymin - MY0;
+            const int x_org = RAW ? xmin : ((xmin - MX0) & ~3), y_org = ymin - MY0;
             const int npx = xmax + MX1 - x_org, rows = ymax + MY1 + 1 - y_org;
             const int gx0 = (3 * x_org) & ~15;                           // TMA: 16-byte aligned byte column
-            const int delta = 3 * x_org - gx0;                           // 0, 4, 8 or 12
+            const int delta = 3 * x_org - gx0;                           // 0, 4, 8 or 12 (RAW: 0 .. 15)
             const int need = delta + 3 * (npx + 1);                      // bytes of a row the records depend on
-            const int wsel = (need + 47) / 48 - 1;                       // box width 48 (wsel + 1)
-            const uint32_t bw = 48u * (uint32_t)(wsel + 1);
+            const int wsel = RAW ? (need + 63) / 64 - 1 : (need + 47) / 48 - 1;   // box width 48 (wsel + 1); RAW: 64 (wsel + 1)
+            const uint32_t bw = (RAW ? 64u : 48u) * (uint32_t)(wsel + 1);
             // one TMA box per frame: the smallest of the three box heights that covers the footprint
             const int hsel = max(0, kTNumBoxH - 1 - (a.rows_max - rows) / kTBoxRows);
             const uint32_t box_rows = (uint32_t)(a.rows_max - kTBoxRows * (kTNumBoxH - 1 - hsel));
@@ -583,10 +627,15 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 } else if (staged) {
                     const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
                     const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
+                    if constexpr (RAW) {
+                        pa[k] = raw_s + ry * bw + (((uint32_t)delta + 3u * rx) & ~3u);  // upper record in raw buffer 0; lower: + bw
+                        pa2[k] = 0; ph[k] = 0; ph2[k] = 0;
+                    } else {
                     pa[k] = dsm_s + off_pairs + ry * ppitch + rx * 4u;                  // shared-window addresses
                     pa2[k] = pa[k] + ppitch;
                     ph[k] = dsm_s + off_hi + ry * (ppitch >> 1) + rx * 2u;
                     ph2[k] = ph[k] + (ppitch >> 1);
+                    }
                     const uint32_t ax0 = 32u - fx, ay0 = (32u - fy) * 64u, ay1 = fy * 64u;
                     pb[k] = min(ay0 * ax0, 65535u) | ((ay0 * fx) << 16);
                     pc[k] = (ay1 * ax0) | ((ay1 * fx) << 16);
@@ -616,9 +665,14 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             // does any lane of this warp ever reload the upper record after its first pixel?  (Never where the
             // source is not minified along y and the source column is constant: most ring / cube tiles.)
             const bool any_a = __any_sync(0xffffffffu, ((pm & ~(3u << (2 * (HC - 1)))) & 0xaaaaaaaau) != 0u);
+            // RAW: byte alignment of this thread's source column (the same for its 8 pixels: column-only map_x)
+            const uint32_t al = RAW ? (((uint32_t)delta + 3u * (uint32_t)((sxs[0] >> 5) - x_org)) & 3u) : 0u;
+            uint32_t sel_lo = 0x4130u + 0x1111u * al, sel_hi = ((al + 6u) & 7u) | (((al + 1u) & 7u) << 4);
+            uint32_t m3 = al == 3u ? 0xffffffffu : 0u;
+            asm volatile("" : "+r"(sel_lo), "+r"(sel_hi), "+r"(m3));
 
             // transform: the flat sequence of 4-pixel groups tid, tid + 128, ... of rows * (bw / 12)
-            const int tgroups = staged ? rows * (int)(bw / 12u) : 0;
+            const int tgroups = (staged && !RAW) ? rows * (int)(bw / 12u) : 0;
             int tn = tgroups > tid ? (tgroups - tid + kTT - 1) / kTT : 0;        // this thread's groups per frame
             asm volatile("" : "+r"(tn));
             uint32_t tsrc0 = kOffRaw + (uint32_t)delta + 12u * tid;                 // in raw buffer 0
@@ -641,7 +695,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     mbar_wait_s(mbar_s + 8u * rb, (phase >> rb) & 1u);
                     phase ^= 1u << rb;
                     uint32_t src = tsrc0 + rb * raw_bytes, dst = tdst0;
-                    if constexpr (LZ) {
+                    if constexpr (RAW) {
+                        (void)src; (void)dst;
+                    } else if constexpr (LZ) {
 #pragma unroll 2
                         for (int i = tid; i < tgroups; i += kTT, src += 12u * kTT, dst += 32u * kTT)
                             transform_group(dsm + src, dsm + dst);
@@ -659,8 +715,10 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     }
                 }
                 // the TMA store of the previous frame must have finished reading the packed tile
-                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();                      // pairs ready, raw consumed, tile buffer free
+                if constexpr (!RAW) {
+                    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncthreads();                  // pairs ready, raw consumed, tile buffer free
+                }
                 if (SCORES && tid == 0 && f > f_begin) {
                     long long s1 = 0, s2 = 0;                 // every warp's partial of frame f-1 is in (barrier above)
 #pragma unroll
@@ -668,12 +726,40 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f - 1) * a.V + v], (unsigned long long)s1);
                     atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f - 1) * a.V + v], (unsigned long long)s2);
                 }
-                uint32_t obase = kOffTile + my_word;
+                const uint32_t tile_off = (RAW && (it & 1u)) ? off_pairs : kOffTile;   // RAW: two packed tiles, alternating
+                uint32_t obase = tile_off + my_word;
                 asm volatile("" : "+r"(obase));
                 uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
                 if (staged) {
-                    if (f + 2 < f_end && tid == kTT - 32) issue_box(f + 2, rb);          // this frame's raw rows are consumed
-                  if constexpr (LZ) {
+                    if (!RAW && f + 2 < f_end && tid == kTT - 32) issue_box(f + 2, rb);  // this frame's raw rows are consumed
+                  if constexpr (RAW) {
+                    uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u), X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);
+                    const uint32_t up = rb * raw_bytes, lw = up + bw;        // this frame's buffer: upper / lower record of pixel k at pa[k] + up / + lw
+                    auto emit = [&](int k, const uint2 &U, const uint2 &V) {
+                        const uint32_t pxl = combine_pairs(U, V, pb[k], pc[k]);
+                        const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
+                        if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
+                    };
+                    auto walk = [&](auto reload) {
+                        constexpr bool A = decltype(reload)::value;
+                        step_raw<HC - 1, true>(X, Y, pa[HC - 1] + up, pa[HC - 1] + lw, sel_lo, sel_hi, pm, m3);          // both records (mode 3)
+                        X2 = X; Y2 = Y;
+                        step_raw<HC, A>(X2, Y2, pa[HC] + up, pa[HC] + lw, sel_lo, sel_hi, pm, m3);
+                        emit(HC - 1, X, Y); emit(HC, X2, Y2);
+                        step_raw<HC - 2, A>(Y, X, pa[HC - 2] + lw, pa[HC - 2] + up, sel_lo, sel_hi, pm, m3);             // upwards: roles swapped
+                        step_raw<HC + 1, A>(X2, Y2, pa[HC + 1] + up, pa[HC + 1] + lw, sel_lo, sel_hi, pm, m3);
+                        emit(HC - 2, X, Y); emit(HC + 1, X2, Y2);
+                        if constexpr (kTP == 8) {
+                            step_raw<1, A>(Y, X, pa[1] + lw, pa[1] + up, sel_lo, sel_hi, pm, m3);
+                            step_raw<6, A>(X2, Y2, pa[6] + up, pa[6] + lw, sel_lo, sel_hi, pm, m3);
+                            emit(1, X, Y); emit(6, X2, Y2);
+                            step_raw<0, A>(Y, X, pa[0] + lw, pa[0] + up, sel_lo, sel_hi, pm, m3);
+                            step_raw<7, A>(X2, Y2, pa[7] + up, pa[7] + lw, sel_lo, sel_hi, pm, m3);
+                            emit(0, X, Y); emit(7, X2, Y2);
+                        }
+                    };
+                    if (any_a) walk(std::true_type{}); else walk(std::false_type{});
+                  } else if constexpr (LZ) {
 #pragma unroll
                     for (int k = 0; k < kTP; ++k) {
                         const uint32_t pxl = lanczos_pairs<true>(dsm, pa[k], ppitch, a.lz_tab, pb[k], wst, lane);
@@ -736,17 +822,20 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     }
                     if (SCORES && hvalid) halo_store_t<TH>(gt, tid, (uint8_t)gray_of(direct(kTP)));
                 }
+                // RAW: the store of the previous frame has read the OTHER tile buffer (the next frame's) before anyone gets there
+                if (RAW && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();                      // tile (+ gray halo) complete; pairs free for the next frame
+                __syncthreads();                      // tile (+ gray halo) complete; pairs / raw rows free for the next frame
+                if (RAW && staged && f + 2 < f_end && tid == kTT - 32) issue_box(f + 2, rb);
 
                 if (a.store_ok) {
-                    if (tid == 0) tma_store_tile(&tms.out, otile_s, x0 * 3, y0, f * a.V + v);
+                    if (tid == 0) tma_store_tile(&tms.out, RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
                 } else {
                     const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(TH, g.oh - y0);
                     uint8_t *out_view = a.out + ((size_t)f * a.V + v) * view_bytes;
                     for (int i = tid; i < TH * kTile * 3; i += kTT) {
                         const int row = i / (kTile * 3), bb = i - row * (kTile * 3);
-                        if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = otile[i];
+                        if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = dsm[tile_off + i];
                     }
                 }
                 if (SCORES) {

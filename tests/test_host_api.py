@@ -227,11 +227,13 @@ def test_plan_preview_capacity(x360):
     pv = x360.plan_preview(2880, 5760, 1600, 90, x360.rotation_stack(views)[1])
     # 32 output rows cover at most 32 * (W / 2 pi) / f = 36.7 source rows (+ the lower tap, + slack)
     assert 38 <= pv["rows_max"] <= 48 and pv["rows_max"] % 8 == 0
-    assert pv["bw_max"] in (96, 144, 192, 240) and pv["tile_h"] == 32
+    assert pv["bw_max"] in (96, 128, 144, 192, 240, 256) and pv["tile_h"] == 32      # 64-byte steps on the raw-gather plans
     # a strongly minifying geometry (11520-wide source, 2048^2 views: 1.8 source px per output px) works in
     # 16-row tiles so that the footprint buffers still leave several CTAs per SM
     views12 = x360.GeometryProcessor.generate_views(12, 0, "ring")
-    assert x360.plan_preview(5760, 11520, 2048, 90, x360.rotation_stack(views12, [0, 3, 6, 9])[1])["tile_h"] == 16
+    pv12 = x360.plan_preview(5760, 11520, 2048, 90, x360.rotation_stack(views12, [0, 3, 6, 9])[1])
+    assert pv12["with_scores"]["tile_h"] == 16                           # pair-record planes (fused score)
+    assert pv12["tile_h"] == 32 and pv12["bw_max"] % 64 == 0             # raw gather: no planes to keep, 32-row tiles fit
     with pytest.raises(x360.X360Error):
         x360.plan_preview(2880, 5760, 1600, 190, x360.rotation_stack(views)[1])
 
