@@ -57,6 +57,10 @@ constexpr int kTNumBoxW = 5;          // load box widths 48, 96, 144, 192, 240 b
 constexpr int kTNumBoxH = 3;          // load box heights rows_max - 16, rows_max - 8, rows_max
 constexpr int kTNumBox = kTNumBoxW * kTNumBoxH;
 constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
+#ifndef X360_RAW_NB
+#define X360_RAW_NB 3
+#endif
+constexpr int kTRawBufs = X360_RAW_NB;   // raw buffers of the raw-gather variant (the TMA box of frame f + NB - 1 flies during frame f)
 
 struct TiledMaps {
     CUtensorMap in[kTNumBox];         // uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]; raw gather: {64 (w + 1), ..}, w < 4
@@ -92,7 +96,7 @@ struct TiledArgs {
 
 struct TiledCtrl {
     int wbb[kTWMax][4];                  // per-warp footprint bounding boxes (16-B aligned rows)
-    unsigned long long mbar[2];       // one per raw buffer
+    unsigned long long mbar[3];       // one per raw buffer
     int wsum[kTWMax][2];                 // per-warp (sum L, sum L^2) of the current frame's tile (exact in 32 bits)
     int item;
 };
@@ -120,14 +124,14 @@ template <int TH> struct TGray {
     uint8_t hr[TH];
 };
 
-__host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return kOffTile + (uint32_t)th * kTile * 3; }          // Q5 map_y: 3 byte planes (< 2^20)
-__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 3; }
+__host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return kOffTile + (uint32_t)th * kTile * 3; }          // Q5 map_y (< 2^20): 2 byte planes + 1 nibble plane
+__host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 5 / 2; }   // 20 bits per value
 // fp64 map_x: a TH x 32 tile, or ONE row of 32 where map_x does not depend on the output row (column-only units)
 __host__ __device__ constexpr uint32_t tiled_off_u0(bool scores, int th)
 {
     return scores ? ((tiled_off_gray(th) + (uint32_t)((th + 2) * kTile + 2 * th) + 127u) & ~127u) : tiled_off_gray(th);
 }
-__host__ __device__ constexpr uint32_t tiled_u0_bytes(int th, bool col_only) { return col_only ? 4u * kTile * 8u : (uint32_t)th * kTile * 8u; }   // column-only: one row per warp
+__host__ __device__ constexpr uint32_t tiled_u0_bytes(int th, bool col_only) { return col_only ? kTile * 8u : (uint32_t)th * kTile * 8u; }   // column-only: one row (every warp writes the same values)
 __host__ __device__ constexpr uint32_t tiled_off_raw(bool scores, int th, bool col_only) { return tiled_off_u0(scores, th) + tiled_u0_bytes(th, col_only); }
 static_assert(tiled_off_gray(32) % 128 == 0 && tiled_off_gray(16) % 128 == 0, "raw buffers must be 128-byte aligned");
 
@@ -142,7 +146,7 @@ __host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max, 
 __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th, bool col_only, bool raw = false)
 {
     // RAW: ctrl | packed tile | map_y | map_x row | raw x2 | second packed tile
-    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3;
+    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + kTRawBufs * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3;
     // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
     return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
            (lanczos ? (size_t)kTWMax * 32 * 144 : 0);
@@ -459,6 +463,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     static_assert(TP == 8 || TP == 4, "the gather is written out for 8 or 4 rows per thread");
     static_assert(NW == 4 || (NW == 2 && !SCORES), "the halo of the fused score needs 64 + 2 TH threads");
     constexpr int kTP = TP;
+    constexpr int NB = RAW ? kTRawBufs : 2;                                         // raw buffers
     constexpr int kTW = NW, kTT = 32 * NW;                                          // warps / threads per CTA
     constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
@@ -470,15 +475,16 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     asm volatile("" : "+r"(kOffRaw));
     uint32_t raw_bytes = tiled_raw_bytes(a.rows_max, a.bw_max);
     asm volatile("" : "+r"(raw_bytes));                                             // keep in a register (cheaper than rematerialising)
-    const uint32_t off_pairs = kOffRaw + 2u * raw_bytes;                            // dsm-relative
+    const uint32_t off_pairs = kOffRaw + (uint32_t)NB * raw_bytes;                  // dsm-relative (RAW: the second packed tile)
     const uint32_t off_hi = off_pairs + tiled_lo_bytes(a.rows_max, a.bw_max);          // bilinear: hi plane after the lo plane
     const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max, LZ) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
     const uint32_t mbar_s = dsm_s + kOffCtl + (uint32_t)offsetof(TiledCtrl, mbar);
 
-    if (tid == 0) { mbar_init(&ctl.mbar[0], 1); mbar_init(&ctl.mbar[1], 1); }
+    if (tid == 0) { mbar_init(&ctl.mbar[0], 1); mbar_init(&ctl.mbar[1], 1); mbar_init(&ctl.mbar[2], 1); }
     uint32_t phase = 0;               // bit b: parity of raw buffer b's mbarrier
+    uint32_t rbn = 0;                 // raw buffer of the next frame (it mod NB)
     uint32_t it = 0;                  // frames processed by this CTA: selects the raw buffer
 
     // frame-invariant: where this lane's packed word of row k goes (+ k * 96), and how it is built
@@ -511,17 +517,19 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
         {
             const double *R = a.R + 9 * a.unit_view[unit.first];
             const int x = min(x0 + lane, g.ow - 1);
+            int sy_hi = 0;
 #pragma unroll 1
             for (int k = 0; k < kTP; ++k) {
                 double v0, v1, v2;
                 map_ray(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), v0, v1, v2);
                 // yaw-only rotations: v0 and v2, hence map_x, do not depend on the row: one atan2 per column and warp
                 if (!col_u0) u0s[k * kTT + tid] = map_u_of(g, v0, v2);
-                else if (k == 0) u0s[tid] = map_u_of(g, v0, v2);
+                else if (k == 0) u0s[lane] = map_u_of(g, v0, v2);
                 const int syq = q5_of(map_y_of(g, v0, v1, v2));            // 0 .. 32 H < 2^20
                 sy_s[k * kTT + tid] = (uint8_t)syq;
                 sy_s[TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 8);
-                sy_s[2 * TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 16);
+                if (k & 1) sy_s[2 * TH * kTile + (k >> 1) * kTT + tid] = (uint8_t)(sy_hi | ((syq >> 16) << 4));   // bits 16-19 of rows k-1, k
+                sy_hi = syq >> 16;
             }
             if (SCORES) {
                 int hx = -1, hy = -1;
@@ -543,10 +551,11 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             int sxs[kTP + 1], sys[kTP + 1];
 #pragma unroll
             for (int k = 0; k < kTP; ++k) {
-                double uu = u0s[col_u0 ? tid : k * kTT + tid] + shift;
+                double uu = u0s[col_u0 ? lane : k * kTT + tid] + shift;
                 if (uu > Wd) uu -= Wd;
                 sxs[k] = q5_of(__double2float_rn(uu));
-                sys[k] = (int)sy_s[k * kTT + tid] | ((int)sy_s[TH * kTile + k * kTT + tid] << 8) | ((int)sy_s[2 * TH * kTile + k * kTT + tid] << 16);
+                sys[k] = (int)sy_s[k * kTT + tid] | ((int)sy_s[TH * kTile + k * kTT + tid] << 8) |
+                         ((((int)sy_s[2 * TH * kTile + (k >> 1) * kTT + tid] >> (4 * (k & 1))) & 15) << 16);
             }
             sxs[kTP] = sxs[0];
             sys[kTP] = sys[0];
@@ -683,14 +692,17 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             auto issue_box = [&](int f, uint32_t b) {                    // one thread: frame f -> raw buffer b
                 tma_issue_box_s(raw_s + b * raw_bytes, tm, gx0, y_org, f, mbar_s + 8u * b, box_rows * bw);
             };
-            if (staged && tid == 0) {                                    // two frames in flight
-                issue_box(f_begin, it & 1u);
-                if (f_begin + 1 < f_end) issue_box(f_begin + 1, (it + 1u) & 1u);
+            if (staged && tid == 0) {                                    // NB frames in flight
+                uint32_t b = rbn;
+#pragma unroll
+                for (int j = 0; j < NB; ++j, b = (b + 1u == (uint32_t)NB) ? 0u : b + 1u)
+                    if (f_begin + j < f_end) issue_box(f_begin + j, b);
             }
 
             // ---- 4. walk the frame chunk ---------------------------------------------------------
             for (int f = f_begin; f < f_end; ++f, ++it) {
-                const uint32_t rb = it & 1u;
+                const uint32_t rb = rbn;
+                rbn = (rbn + 1u == (uint32_t)NB) ? 0u : rbn + 1u;
                 if (staged) {
                     mbar_wait_s(mbar_s + 8u * rb, (phase >> rb) & 1u);
                     phase ^= 1u << rb;
@@ -826,7 +838,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (RAW && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();                      // tile (+ gray halo) complete; pairs / raw rows free for the next frame
-                if (RAW && staged && f + 2 < f_end && tid == kTT - 32) issue_box(f + 2, rb);
+                if (RAW && staged && f + NB < f_end && tid == kTT - 32) issue_box(f + NB, rb);
 
                 if (a.store_ok) {
                     if (tid == 0) tma_store_tile(&tms.out, RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
