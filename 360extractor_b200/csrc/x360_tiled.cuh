@@ -484,7 +484,8 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
 
     if (tid == 0) { mbar_init(&ctl.mbar[0], 1); mbar_init(&ctl.mbar[1], 1); mbar_init(&ctl.mbar[2], 1); }
     uint32_t phase = 0;               // bit b: parity of raw buffer b's mbarrier
-    uint32_t rbn = 0;                 // raw buffer of the next frame (it mod NB)
+    uint32_t rbn = 0;                 // raw buffer of the next frame (it mod NB; RAW: of the next STAGED frame)
+    uint32_t rpar = 0;                // RAW: mbarrier parity of the current round through the raw buffers
     uint32_t it = 0;                  // frames processed by this CTA: selects the raw buffer
 
     // frame-invariant: where this lane's packed word of row k goes (+ k * 96), and how it is built
@@ -492,6 +493,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     uint32_t pack_sel = q == 0 ? 0x4210u : (q == 1 ? 0x5421u : 0x6542u);
     uint32_t my_word = (uint32_t)(warp * kTP) * (kTile * 3) + (uint32_t)((lane >> 2) * 3 + q) * 4u;
     asm volatile("" : "+r"(pack_sel), "+r"(my_word));      // keep both in registers: rematerialising them costs more than the gather
+    // RAW: shared-window address of this lane's word in the current packed tile, flipped between the two tiles per frame
+    uint32_t ot = dsm_s + kOffTile + my_word, ot_toggle = RAW ? (ot ^ (dsm_s + off_pairs + my_word)) : 0u;
+    asm volatile("" : "+r"(ot), "+r"(ot_toggle));
     const int tiles_per_view = g.tiles_x * a.tiles_y;
     const double Wd = (double)g.W;
 
@@ -702,10 +706,15 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             // ---- 4. walk the frame chunk ---------------------------------------------------------
             for (int f = f_begin; f < f_end; ++f, ++it) {
                 const uint32_t rb = rbn;
-                rbn = (rbn + 1u == (uint32_t)NB) ? 0u : rbn + 1u;
+                if (!RAW || staged) rbn = (rbn + 1u == (uint32_t)NB) ? 0u : rbn + 1u;
                 if (staged) {
+                    if constexpr (RAW) {                                  // buffers are used in cyclic order: one parity per round
+                        mbar_wait_s(mbar_s + 8u * rb, rpar);
+                        if (rbn == 0u) rpar ^= 1u;
+                    } else {
                     mbar_wait_s(mbar_s + 8u * rb, (phase >> rb) & 1u);
                     phase ^= 1u << rb;
+                    }
                     uint32_t src = tsrc0 + rb * raw_bytes, dst = tdst0;
                     if constexpr (RAW) {
                         (void)src; (void)dst;
@@ -740,7 +749,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 }
                 const uint32_t tile_off = (RAW && (it & 1u)) ? off_pairs : kOffTile;   // RAW: two packed tiles, alternating
                 uint32_t obase = tile_off + my_word;
-                asm volatile("" : "+r"(obase));
+                if (!(RAW && staged)) asm volatile("" : "+r"(obase));
                 uint32_t *const orow = reinterpret_cast<uint32_t *>(dsm + obase);
                 if (staged) {
                     if (!RAW && f + 2 < f_end && tid == kTT - 32) issue_box(f + 2, rb);  // this frame's raw rows are consumed
@@ -750,7 +759,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     auto emit = [&](int k, const uint2 &U, const uint2 &V) {
                         const uint32_t pxl = combine_pairs(U, V, pb[k], pc[k]);
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
-                        if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
+                        if (q != 3) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ot + (uint32_t)(k * kTile * 3)), "r"(__byte_perm(pxl, nb, pack_sel)) : "memory");
                     };
                     auto walk = [&](auto reload) {
                         constexpr bool A = decltype(reload)::value;
@@ -835,14 +844,19 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     if (SCORES && hvalid) halo_store_t<TH>(gt, tid, (uint8_t)gray_of(direct(kTP)));
                 }
                 // RAW: the store of the previous frame has read the OTHER tile buffer (the next frame's) before anyone gets there
-                if (RAW && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // (every thread executes the wait — only thread 0 has bulk groups — which saves the branch around it)
+                if (RAW) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();                      // tile (+ gray halo) complete; pairs / raw rows free for the next frame
-                if (RAW && staged && f + NB < f_end && tid == kTT - 32) issue_box(f + NB, rb);
+                if constexpr (RAW) ot ^= ot_toggle;
 
                 if (a.store_ok) {
-                    if (tid == 0) tma_store_tile(&tms.out, RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
+                    if (tid == 0) {
+                        if (RAW && staged && f + NB < f_end) issue_box(f + NB, rb);
+                        tma_store_tile(&tms.out, RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
+                    }
                 } else {
+                    if (RAW && staged && f + NB < f_end && tid == 0) issue_box(f + NB, rb);
                     const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(TH, g.oh - y0);
                     uint8_t *out_view = a.out + ((size_t)f * a.V + v) * view_bytes;
                     for (int i = tid; i < TH * kTile * 3; i += kTT) {
