@@ -150,15 +150,17 @@ int tiled_warps(bool, int) { return 4; }
 
 // The raw gather (no transform, x360_tiled.cuh RAW) serves the plans of the 7-CTA variant: bilinear, 32x32 tiles,
 // column-only map_x, no fused score.  X360_NO_RAW=1 keeps them on the pair-record planes.
-bool tiled_raw(bool scores, bool lanczos, int th, bool col)
+// (The variable is read when a plan is created or previewed; the plan remembers the answer.)
+bool raw_allowed()
 {
-    static const bool off = [] { const char *e = getenv("X360_NO_RAW"); return e && atoi(e); }();
-    return col && !scores && !lanczos && th == 32 && !off;
+    const char *e = getenv("X360_NO_RAW");
+    return !(e && atoi(e));
 }
+bool tiled_raw(bool scores, bool lanczos, int th, bool col, bool allow) { return allow && col && !scores && !lanczos && th == 32; }
 
-tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col = false)
+tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col, bool raw)
 {
-    if (tiled_raw(scores, lanczos, th, col)) return extract_tiled<false, false, 8, 4, 7, true>;
+    if (raw) return extract_tiled<false, false, 8, 4, 7, true>;
     if (col && !scores && !lanczos && th == 32) return extract_tiled<false, false, 8, 4, 7>;
     if (th == 16) {
         if (lanczos) return scores ? extract_tiled<true, true, 4, 4> : extract_tiled<false, true, 4, 4>;
@@ -281,7 +283,7 @@ bool column_only_map_x(const double *R, int V)
     return V > 0;
 }
 
-void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, int *rows_out, int *bw_out, int *tile_h_out)
+void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, bool allow_raw, int *rows_out, int *bw_out, int *tile_h_out)
 {
     const bool col = column_only_map_x(R, V);
     // measured on cfg2 (B200): 4 CTAs/SM 0.92, 5 CTAs 1.0, 6 CTAs 1.10; fewer CTAs hide less latency
@@ -293,7 +295,7 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
     if (const char *e = getenv("X360_TILED_TH")) forced_th = atoi(e);
     for (int th = 32; th >= 16; th -= 16) {
         if (forced_th && forced_th != th) continue;
-        const bool raw = tiled_raw(scores, lanczos, th, col);
+        const bool raw = tiled_raw(scores, lanczos, th, col, allow_raw);
         std::vector<int> rows, bws;
         size_t total = 0;
         const int tiles_y = (g.oh + th - 1) / th;
@@ -359,6 +361,7 @@ struct x360_plan {
     // tiled path
     bool col_u0 = false;                 // map_x depends on the output column only (yaw-only rotations)
     int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with scores
+    bool t_raw[2] = {false, false};      // the launch takes the raw-gather variant (no transform)
     // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
     // coarsest one that still yields enough work items without cutting the frame batch into chunks
     int n_units[4] = {0, 0, 0, 0};
@@ -382,7 +385,7 @@ static int plan_grid(const x360_plan *pl, bool scores)
     int occ = 0;
     cudaError_t e;
     if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th[scores ? 1 : 0], pl->col_u0), 32 * tiled_warps(scores, pl->t_th[scores ? 1 : 0]), pl->t_smem[scores ? 1 : 0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th[scores ? 1 : 0], pl->col_u0, pl->t_raw[scores ? 1 : 0]), 32 * tiled_warps(scores, pl->t_th[scores ? 1 : 0]), pl->t_smem[scores ? 1 : 0]);
         if (e != cudaSuccess || occ < 1) occ = 1;
         return pl->sm_count * occ;                 // capped by the item count at launch
     } else if (pl->path == X360_PATH_STAGED)
@@ -455,7 +458,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     memset(&tms, 0, sizeof tms);
     if ((a.stage_ok || a.store_ok) &&
         !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, t_th, a.store_ok != 0, &tms,
-                           tiled_raw(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0))) {
+                           pl->t_raw[sc])) {
         a.stage_ok = 0;                                   // every tile goes direct, byte stores
         a.store_ok = 0;
     }
@@ -465,7 +468,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0)<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, tms);
+    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0, pl->t_raw[sc])<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
@@ -505,7 +508,7 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
     for (int sc = 0; sc < 2; ++sc) {
         int rows = 0, bw = 0, th = 0;
         choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
-                        params->n_views, params->interp == X360_INTERP_LANCZOS4, sc != 0, &rows, &bw, &th);
+                        params->n_views, params->interp == X360_INTERP_LANCZOS4, sc != 0, raw_allowed(), &rows, &bw, &th);
         if (rows_max) rows_max[sc] = rows;
         if (bw_max) bw_max[sc] = bw;
         if (tile_h) tile_h[sc] = th;
@@ -550,10 +553,12 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         // staging capacity and tile height from a host survey of the tiles' footprints, without / with the score halo
         const bool lz = params->interp == X360_INTERP_LANCZOS4;
         pl->col_u0 = column_only_map_x(params->R, params->n_views) && !(getenv("X360_NO_COL_U0") && atoi(getenv("X360_NO_COL_U0")));
+        const bool allow_raw = raw_allowed() && pl->col_u0;
         for (int sc = 0; sc < 2; ++sc) {
             int rows = 40, bw = 144, th = 32;
-            choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, &rows, &bw, &th);
-            const bool raw = tiled_raw(sc != 0, lz, th, pl->col_u0);
+            choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, allow_raw, &rows, &bw, &th);
+            const bool raw = tiled_raw(sc != 0, lz, th, pl->col_u0, allow_raw);
+            pl->t_raw[sc] = raw;
             if (const char *e = getenv("X360_TILED_BW")) {
                 const int v = atoi(e), unit = raw ? 64 : 48;
                 bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
@@ -564,7 +569,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
             pl->t_bw[sc] = bw;
             pl->t_rows[sc] = rows;
             pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0, raw), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
             if (ea != cudaSuccess) {
                 const size_t want = pl->t_smem[sc];
                 delete pl;

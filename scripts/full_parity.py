@@ -31,14 +31,16 @@ for name, (H, W), layout, n, pitch, active, d, fov, mode in CONFIGS:
     with x360.Extractor(H, W, d, fov, R, mode) as ex:
         got, s, s2 = ex.extract_sums(frame)
         modes = ex.tile_modes()
+        plain, _ = ex.extract(frame, want_scores=False)       # the kernel variant without the fused score (cfg2: the raw gather)
     diff_bytes = 0
     sum_mismatch = 0
     for v in range(len(names)):
         want, ws, ws2 = c_oracle.extract(frame, R[v:v + 1], d, fov, interp)
         diff_bytes += int(np.count_nonzero(got[0, v] != want[0, 0]))
         sum_mismatch += int(s[0, v] != ws[0, 0]) + int(s2[0, v] != ws2[0, 0])
+    diff_bytes += int(np.count_nonzero(plain != got))
     case = {"config": name, "src": [W, H], "layout": layout, "views": len(names), "pitch": pitch, "out": d, "interp": mode,
-            "bytes_compared": int(got.size), "differing_bytes": diff_bytes, "laplacian_sum_mismatches": sum_mismatch,
+            "bytes_compared": 2 * int(got.size), "differing_bytes": diff_bytes, "laplacian_sum_mismatches": sum_mismatch,
             "tile_modes": modes, "seconds": round(time.time() - t0, 1)}
     print(case, flush=True)
     report["cases"].append(case)

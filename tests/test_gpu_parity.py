@@ -114,6 +114,41 @@ def test_sweep_against_oracle(x360, oracle, cfg, mode, interp, path):
     assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
 
 
+# ---- the raw-gather variant (bilinear, column-only map_x, no fused score) and the pair-record planes it replaced --------
+RAW_CASES = [
+    # (H, W, d, fov, n, F)
+    (512, 1024, 256, 90, 8, 7),        # 1.27 source px per output px; 7 frames: the three raw buffers wrap around twice
+    (480, 960, 250, 90, 6, 5),         # partial tiles, output pitch not a multiple of 16 B: byte stores instead of the TMA store
+    (720, 1440, 512, 100, 4, 4),
+    (360, 720, 288, 60, 3, 3),         # magnification: records shared by neighbouring lanes
+    (1440, 2880, 800, 90, 8, 5),       # cfg2 at half size
+    (300, 600, 128, 90, 4, 3),         # frame pitch not a multiple of 16 B: no TMA loads, every tile takes the direct gathers
+]
+
+
+@pytest.mark.parametrize("no_raw", ["0", "1"], ids=["raw", "planes"])
+@pytest.mark.parametrize("cfg", RAW_CASES)
+def test_raw_gather_ring_plans(x360, oracle, monkeypatch, cfg, no_raw):
+    H, W, d, fov, n, F = cfg
+    monkeypatch.setenv("X360_NO_RAW", no_raw)           # read when the plan is created
+    frames = np.stack([noise_frame(300 + i, H, W) for i in range(F)])
+    views = x360.GeometryProcessor.generate_views(n, 0, "ring")
+    R = rotations(x360, views)
+    assert x360.column_only_map_x(R)
+    want, _, _ = oracle.extract(frames, R, d, fov, 0, want_scores=False)
+    with x360.Extractor(H, W, d, fov, R, "linear", max_batch=F) as ex:
+        got, none = ex.extract(frames, want_scores=False)
+        modes = ex.tile_modes()
+        again, _ = ex.extract(frames, want_scores=False)
+    assert none is None
+    assert_same(got, want, f"{cfg} no_raw={no_raw}")
+    assert np.array_equal(got, again)
+    if (W * 3) % 16 == 0:
+        assert modes["staged"] > 0.5 * sum(modes.values()), modes
+    else:
+        assert modes["staged"] == 0
+
+
 def test_roll_and_active_camera_subset(x360, oracle):
     views = x360.GeometryProcessor.generate_views(12, 0, "ring")
     names, R = x360.rotation_stack(views, active_cameras=[0, 3, 6, 9])
