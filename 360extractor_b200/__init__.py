@@ -13,6 +13,7 @@ from .analyzer import BlurAnalyzer
 from .blur_filter import BlurFilter
 from .extractor import Extractor, PinnedBuffer, column_only_map_x, plan_preview, remap, scores_from_sums
 from .geometry import GeometryProcessor, focal_length, rotation_stack
+from .handoff import eligible_indices, masker_input, masker_slots, normalize_mask_faces, scatter_results
 from .image_utils import ImageUtils
 from .pipeline import ExtractionSession, ViewResult
 from .sharding import gather_sums, shard_bounds, shard_sizes
@@ -24,5 +25,6 @@ __all__ = [
     "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "BlurAnalyzer",
     "PinnedBuffer", "column_only_map_x", "plan_preview", "remap", "unsharp_mask", "unsharp_mask_device", "scores_from_sums", "rotation_stack", "focal_length",
     "gather_sums", "shard_bounds", "shard_sizes",
+    "normalize_mask_faces", "eligible_indices", "masker_slots", "masker_input", "scatter_results",
     "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",
 ]

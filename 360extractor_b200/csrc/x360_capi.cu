@@ -1013,6 +1013,39 @@ int x360_unsharp_host(int32_t device, const uint8_t *images, int64_t n_images, i
     return rc;
 }
 
+int x360_views_to_nchw(int32_t device, const uint8_t *views, int64_t n_views, int32_t h, int32_t w, const int32_t *select,
+                       int32_t n_select, int32_t to_rgb, float *out, void *cuda_stream)
+{
+    if (!views || !out) return fail(X360_E_INVALID, "null argument");
+    if (h < 1 || w < 1 || n_views < 0 || n_select < 0) return fail(X360_E_INVALID, "bad shape %lld x %d x %d, %d selected", (long long)n_views, h, w, n_select);
+    const long long total = select ? n_select : n_views;
+    for (int i = 0; select && i < n_select; ++i)
+        if (select[i] < 0 || select[i] >= n_views) return fail(X360_E_INVALID, "select[%d] = %d outside [0, %lld)", i, select[i], (long long)n_views);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    if (total == 0) return X360_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t hw = (size_t)h * w, view_bytes = hw * 3;
+    const bool fast = hw % 4 == 0 && (uintptr_t)views % 4 == 0 && (uintptr_t)out % 16 == 0;
+    for (long long n0 = 0; n0 < total; n0 += 64) {
+        NchwSel sel;
+        const int m = (int)std::min<long long>(64, total - n0);
+        for (int i = 0; i < m; ++i) sel.idx[i] = select ? select[n0 + i] : (int)(n0 + i);
+        float *o = out + (size_t)n0 * 3 * hw;
+        if (fast) {
+            const int groups = (int)(hw / 4);
+            views_to_nchw_kernel<<<dim3((unsigned)((groups + 255) / 256), (unsigned)m), 256, 0, st>>>(views, view_bytes, groups, sel, o, to_rgb);
+        } else {
+            views_to_nchw_generic<<<dim3((unsigned)((hw + 255) / 256), (unsigned)m), 256, 0, st>>>(views, view_bytes, hw, sel, o, to_rgb);
+        }
+        g_launches.fetch_add(1);
+        CU(cudaGetLastError());
+    }
+    return X360_OK;
+}
+
 int x360_host_alloc(size_t bytes, void **out_ptr)
 {
     if (!out_ptr) return fail(X360_E_INVALID, "null argument");

@@ -1,5 +1,5 @@
 // x360_misc.cuh — the small entry points around the hot path: materialised maps,
-// explicit-map remap, stand-alone blur sums.  These exist so that every reference call
+// explicit-map remap, stand-alone blur sums, the device-resident hand-off to the masker.  These exist so that every reference call
 // signature on the path stays callable on the GPU; none of them is on the batch hot path.
 #pragma once
 #include "x360_common.cuh"
@@ -80,6 +80,49 @@ laplacian_sums_kernel(const uint8_t *__restrict__ gray, int h, int w, long long 
         atomicAdd((unsigned long long *)sum, (unsigned long long)pl);
         atomicAdd((unsigned long long *)sum2, (unsigned long long)pl2);
     }
+}
+
+// hand the views of the selected faces to the masker without leaving the device.
+// src/core/processor.py:392-420 passes the BGR views (all of them, or the faces named in 'ai_mask_cameras') to
+// AIService.process_batch (src/core/ai_model.py:125-167), whose model turns each image into a normalised
+// CHW float tensor (BGR -> RGB, HWC -> CHW, / 255).  Here: uint8 [.][h][w][3] views in device memory ->
+// float32 [n_sel][3][h][w]; value = float(v) / 255 correctly rounded (what numpy's float32 division gives).
+struct NchwSel {
+    int idx[64];                       // view slots (flat [frame * V + view]) of this launch
+};
+
+__device__ __forceinline__ float u8_to_unit(uint32_t v) { return __fdiv_rn((float)v, 255.0f); }
+
+// one thread per 4 pixels: 12 packed bytes in (3 LDG.32), one float4 to each of the three planes
+__global__ void __launch_bounds__(256)
+views_to_nchw_kernel(const uint8_t *__restrict__ views, size_t view_bytes, int groups, const NchwSel sel, float *__restrict__ out,
+                     int to_rgb)
+{
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= groups) return;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(views + (size_t)sel.idx[blockIdx.y] * view_bytes) + 3 * (size_t)g;
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);       // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+    const float4 cb = make_float4(u8_to_unit(w0 & 255u), u8_to_unit(w0 >> 24), u8_to_unit((w1 >> 16) & 255u), u8_to_unit((w2 >> 8) & 255u));
+    const float4 cg = make_float4(u8_to_unit((w0 >> 8) & 255u), u8_to_unit(w1 & 255u), u8_to_unit(w1 >> 24), u8_to_unit((w2 >> 16) & 255u));
+    const float4 cr = make_float4(u8_to_unit((w0 >> 16) & 255u), u8_to_unit((w1 >> 8) & 255u), u8_to_unit(w2 & 255u), u8_to_unit(w2 >> 24));
+    const size_t hw = (size_t)groups * 4;
+    float4 *o = reinterpret_cast<float4 *>(out + (size_t)blockIdx.y * 3 * hw) + g;
+    o[0] = to_rgb ? cr : cb;
+    o[hw / 4] = cg;
+    o[2 * (hw / 4)] = to_rgb ? cb : cr;
+}
+
+// any size / alignment: one thread per pixel
+__global__ void __launch_bounds__(256)
+views_to_nchw_generic(const uint8_t *__restrict__ views, size_t view_bytes, size_t hw, const NchwSel sel, float *__restrict__ out, int to_rgb)
+{
+    const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= hw) return;
+    const uint8_t *px = views + (size_t)sel.idx[blockIdx.y] * view_bytes + 3 * p;
+    float *o = out + (size_t)blockIdx.y * 3 * hw + p;
+    o[0] = u8_to_unit(px[to_rgb ? 2 : 0]);
+    o[hw] = u8_to_unit(px[1]);
+    o[2 * hw] = u8_to_unit(px[to_rgb ? 0 : 2]);
 }
 
 }  // namespace x360

@@ -150,6 +150,18 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
                       int32_t *rows_max, int32_t *bw_max, int32_t *tile_h);
 
 /*
+ * Device-resident hand-off of a view batch to the masker: replaces the host round trip of
+ * src/core/processor.py:392-420 (views -> AIService.process_batch, src/core/ai_model.py:125-167, whose model
+ * normalises each BGR image to a CHW float tensor: BGR -> RGB, HWC -> CHW, / 255).
+ * views: DEVICE uint8 [n_views][h][w][3] (the output of x360_extract_device, flat over frames and views);
+ * select: HOST array of n_select view slots to convert — the faces 'ai_mask_cameras' names, processor.py:405-408 —
+ * or NULL for all n_views in order; out: DEVICE float32 [n_select or n_views][3][h][w], value = float(v) / 255
+ * (correctly rounded); to_rgb != 0 swaps B and R.  Asynchronous on cuda_stream.
+ */
+int x360_views_to_nchw(int32_t device, const uint8_t *views, int64_t n_views, int32_t h, int32_t w,
+                       const int32_t *select, int32_t n_select, int32_t to_rgb, float *out, void *cuda_stream);
+
+/*
  * Unsharp mask on a batch of views, the step after the blur filter:
  *   gaussian = cv2.GaussianBlur(rect_img, (0, 0), 2.0)
  *   rect_img = cv2.addWeighted(rect_img, 1.0 + strength, gaussian, -strength, 0)

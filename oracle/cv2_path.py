@@ -17,6 +17,11 @@ Follows (relative to /root/reference):
   blur_score          src/utils/image_utils.py:6-27
   extract             src/core/processor.py:245-265 (maps once per job) and
                       :327-342 (per frame, per view remap [+ score])
+  masker_tensor       src/core/processor.py:392-420 -> src/core/ai_model.py:145 (``self.model(images, ...)``): the
+                      model's input normalisation lives in third-party ``ultralytics`` (requirements.txt, unpinned,
+                      absent here); its published ``BasePredictor.preprocess`` is ``im[..., ::-1].transpose(0, 3, 1, 2)``,
+                      ``.float()``, ``/= 255`` — restated with numpy float32 (no letterbox: views are square and the
+                      device hand-off keeps their size)
 """
 from __future__ import annotations
 
@@ -130,3 +135,13 @@ def unsharp(image, strength):
     import cv2
     gaussian = cv2.GaussianBlur(image, (0, 0), 2.0)
     return cv2.addWeighted(image, 1.0 + strength, gaussian, -strength, 0)
+
+
+def masker_tensor(images, to_rgb=True):
+    """uint8 BGR [N][h][w][3] -> float32 [N][3][h][w] in [0, 1] (RGB unless ``to_rgb=False``)."""
+    im = np.asarray(images, dtype=np.uint8)
+    if to_rgb:
+        im = im[..., ::-1]
+    im = np.ascontiguousarray(im.transpose(0, 3, 1, 2)).astype(np.float32)
+    im /= np.float32(255)
+    return im

@@ -402,3 +402,32 @@ def test_extract_host_with_sharpening_is_extract_then_unsharp(x360, oracle):
     for f in range(5):
         for v in range(6):
             assert np.array_equal(sharp[f, v], oracle.unsharp(plain[f, v], 0.6)), (f, v)
+
+
+# ---- device-resident hand-off to the masker (processor.py:392-420) ------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,n,F", [(64, 6, 2), (50, 6, 1), (33, 36, 3)])     # 33 / 50: the any-size kernel; 36 x 3 = 108 slots: two launches
+def test_masker_handoff_stays_on_the_device(x360, oracle, d, n, F):
+    torch = pytest.importorskip("torch")
+    from oracle import cv2_path
+    H, W = 128, 256
+    layout = "cube" if n == 6 else "ring"
+    views = x360.GeometryProcessor.generate_views(n, 0, layout)
+    names, R = x360.rotation_stack(views)
+    frames = np.stack([noise_frame(700 + i, H, W) for i in range(F)])
+    want_views, _, _ = oracle.extract(frames, R, d, 90, 0, want_scores=False)
+    fr = torch.from_numpy(frames).cuda()
+    out = torch.empty((F, len(names), d, d, 3), dtype=torch.uint8, device="cuda")
+    with x360.Extractor(H, W, d, 90, R, "linear") as ex:
+        ex.extract_device(fr, out, stream=torch.cuda.current_stream())
+        for cams, rgb in ((None, True), ("Up,down" if n == 6 else "view_1, VIEW_7", True), (None, False)):
+            slots, t = x360.masker_input(out, names, cams, to_rgb=rgb)
+            torch.cuda.synchronize()
+            flat = want_views.reshape(F * len(names), d, d, 3)
+            assert slots == x360.masker_slots(F, names, cams)
+            assert t.shape == (len(slots), 3, d, d) and t.dtype == torch.float32 and t.is_cuda
+            want = cv2_path.masker_tensor(flat[slots], to_rgb=rgb) if slots else np.empty((0, 3, d, d), np.float32)
+            assert np.array_equal(t.cpu().numpy(), want), f"hand-off differs (cams={cams}, rgb={rgb})"
+    if n == 6:
+        assert x360.masker_slots(F, names, "Up,down") == [f * 6 + v for f in range(F) for v in (4, 5)]

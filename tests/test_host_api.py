@@ -5,6 +5,7 @@ same calls, same expectations, against the drop-in class."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -256,3 +257,32 @@ def test_column_only_map_x(x360, oracle):
     R = x360.GeometryProcessor.get_rotation_matrix(135.0, 0.0, 0.0)
     mx, _ = oracle.make_map(180, 360, 48, 48, 90, R)
     assert x360.column_only_map_x(R[None]) and np.all(mx == mx[0:1])
+
+
+# ---- device hand-off to the masker: host-side selection logic -------------------------------
+def test_mask_face_selection_mirrors_reference(x360):
+    cases = [None, [], "", "Front, back", ["Up", " down "], "  ,", ["FRONT"], "left"]
+    want = [None, None, None, {"front", "back"}, {"up", "down"}, None, {"front"}, {"left"}]
+    for c, w in zip(cases, want):
+        assert x360.normalize_mask_faces(c) == w
+    ref_src = "/root/reference/src"
+    if os.path.exists(os.path.join(ref_src, "core", "settings_manager.py")):        # the reference itself, where it exists
+        sys.path.insert(0, ref_src)
+        try:
+            from core.settings_manager import normalize_mask_faces as ref_norm
+            for c in cases:
+                assert x360.normalize_mask_faces(c) == ref_norm(c)
+        finally:
+            sys.path.remove(ref_src)
+    names = ["Front", "Right", "Back", "Left", "Up", "Down"]
+    assert x360.eligible_indices(names, None) == [0, 1, 2, 3, 4, 5]
+    assert x360.eligible_indices(names, {"front", "down"}) == [0, 5]             # processor.py:405-408, case-insensitive
+    assert x360.eligible_indices(names, {"nothing"}) == []
+    # 2 frames x 6 views, only Up / Down masked, frame 1's Up view rejected by the blur filter
+    keep = np.ones((2, 6), bool)
+    keep[1, 4] = False
+    assert x360.masker_slots(2, names, "up,down") == [4, 5, 10, 11]
+    assert x360.masker_slots(2, names, "up,down", keep) == [4, 5, 11]
+    assert x360.masker_slots(1, names) == [0, 1, 2, 3, 4, 5]
+    res = x360.scatter_results([4, 5], [("imgU", "maskU"), ("imgD", "maskD")], [f"img{i}" for i in range(6)])
+    assert res[0] == ("img0", None) and res[4] == ("imgU", "maskU") and res[5] == ("imgD", "maskD") and len(res) == 6
