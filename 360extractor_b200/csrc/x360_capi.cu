@@ -148,19 +148,22 @@ typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 // CTAs, was measured too: equal on cfg2, 20-25 % slower where footprints are large — half the warps per SM.)
 int tiled_warps(bool, int) { return 4; }
 
-// The raw gather (no transform, x360_tiled.cuh RAW) serves the plans of the 7-CTA variant: bilinear, 32x32 tiles,
-// column-only map_x, no fused score.  X360_NO_RAW=1 keeps them on the pair-record planes.
+// The raw gather (no transform, x360_tiled.cuh RAW) serves the bilinear plans without a fused score.
+// X360_NO_RAW=1 keeps them on the pair-record planes.
 // (The variable is read when a plan is created or previewed; the plan remembers the answer.)
 bool raw_allowed()
 {
     const char *e = getenv("X360_NO_RAW");
     return !(e && atoi(e));
 }
-bool tiled_raw(bool scores, bool lanczos, int th, bool col, bool allow) { return allow && col && !scores && !lanczos && th == 32; }
+bool tiled_raw(bool scores, bool lanczos, int, bool, bool allow) { return allow && !scores && !lanczos; }
 
 tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col, bool raw)
 {
-    if (raw) return extract_tiled<false, false, 8, 4, 7, true>;
+    if (raw) {                          // bilinear, no fused score: selectors per thread (column-only map_x) or per pixel
+        if (th == 16) return col ? extract_tiled<false, false, 4, 4, 7, true, true> : extract_tiled<false, false, 4, 4, 7, true, false>;
+        return col ? extract_tiled<false, false, 8, 4, 7, true, true> : extract_tiled<false, false, 8, 4, X360_MINB8, true, false>;
+    }
     if (col && !scores && !lanczos && th == 32) return extract_tiled<false, false, 8, 4, 7>;
     if (th == 16) {
         if (lanczos) return scores ? extract_tiled<true, true, 4, 4> : extract_tiled<false, true, 4, 4>;
@@ -553,7 +556,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         // staging capacity and tile height from a host survey of the tiles' footprints, without / with the score halo
         const bool lz = params->interp == X360_INTERP_LANCZOS4;
         pl->col_u0 = column_only_map_x(params->R, params->n_views) && !(getenv("X360_NO_COL_U0") && atoi(getenv("X360_NO_COL_U0")));
-        const bool allow_raw = raw_allowed() && pl->col_u0;
+        const bool allow_raw = raw_allowed();
         for (int sc = 0; sc < 2; ++sc) {
             int rows = 40, bw = 144, th = 32;
             choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, allow_raw, &rows, &bw, &th);

@@ -445,9 +445,10 @@ __host__ __device__ constexpr int tiled_min_ctas(bool scores, bool lz, int tp, i
 //
 // RAW: no transform and no pair-record planes — the gather reads the TMA box itself (step_raw), the footprint rows
 // are 64 k bytes wide, the packed output tile is double-buffered (second copy after the raw buffers) and a frame
-// costs ONE block barrier.  Bilinear, column-only map_x (every pixel of a thread's column has the same byte
-// alignment in its source row, so the two PRMT selectors are per-thread constants), no fused score.
-template <bool SCORES, bool LZ, int TP, int NW, int MINB = tiled_min_ctas(SCORES, LZ, TP, NW), bool RAW = false>
+// costs ONE block barrier.  Bilinear, no fused score.  COLSEL: column-only map_x — every pixel of a thread's column
+// has the same byte alignment in its source row, so the two PRMT selectors and the a = 3 mask are per-thread
+// constants; otherwise they travel per pixel in one register (selector lo | selector hi << 16 | (a = 3) << 31).
+template <bool SCORES, bool LZ, int TP, int NW, int MINB = tiled_min_ctas(SCORES, LZ, TP, NW), bool RAW = false, bool COLSEL = true>
 __global__ void __launch_bounds__(32 * NW, MINB)
 extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
@@ -624,6 +625,9 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             const uint32_t ppitch = (bw / 3u) * (LZ ? 8u : 4u);                  // Lanczos4 record rows / bilinear lo-plane rows
             uint32_t pa[kTP + 1], pa2[kTP + 1], ph[kTP + 1], ph2[kTP + 1], pb[kTP + 1], pc[kTP + 1];   // pa/pa2: lo plane, ph/ph2: hi plane
             pa[kTP] = pa2[kTP] = ph[kTP] = ph2[kTP] = pb[kTP] = pc[kTP] = 0;
+            uint32_t psel[kTP + 1];                                              // RAW without COLSEL: per-pixel selectors
+#pragma unroll
+            for (int k = 0; k <= kTP; ++k) psel[k] = 0;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 if constexpr (LZ) {
@@ -641,8 +645,13 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
                     const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
                     if constexpr (RAW) {
-                        pa[k] = raw_s + ry * bw + (((uint32_t)delta + 3u * rx) & ~3u);  // upper record in raw buffer 0; lower: + bw
+                        const uint32_t o = (uint32_t)delta + 3u * rx;
+                        pa[k] = raw_s + ry * bw + (o & ~3u);                            // upper record in raw buffer 0; lower: + bw
                         pa2[k] = 0; ph[k] = 0; ph2[k] = 0;
+                        if constexpr (!COLSEL) {
+                            const uint32_t al_k = o & 3u;
+                            psel[k] = (0x4130u + 0x1111u * al_k) | ((((al_k + 6u) & 7u) | (((al_k + 1u) & 7u) << 4)) << 16) | (al_k == 3u ? 0x80000000u : 0u);
+                        }
                     } else {
                     pa[k] = dsm_s + off_pairs + ry * ppitch + rx * 4u;                  // shared-window addresses
                     pa2[k] = pa[k] + ppitch;
@@ -761,21 +770,30 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ot + (uint32_t)(k * kTile * 3)), "r"(__byte_perm(pxl, nb, pack_sel)) : "memory");
                     };
+                    auto st = [&](auto kc, auto ac, uint2 &P, uint2 &Q, bool up_walk) {
+                        constexpr int K = decltype(kc)::value;
+                        constexpr bool A = decltype(ac)::value;
+                        const uint32_t slo = COLSEL ? sel_lo : psel[K];                       // (PRMT reads bits 0-15 of its selector)
+                        const uint32_t shi = COLSEL ? sel_hi : (psel[K] >> 16);
+                        const uint32_t msk = COLSEL ? m3 : (uint32_t)((int)psel[K] >> 31);
+                        if (up_walk) step_raw<K, A>(P, Q, pa[K] + lw, pa[K] + up, slo, shi, pm, msk);        // upwards: roles swapped
+                        else step_raw<K, A>(P, Q, pa[K] + up, pa[K] + lw, slo, shi, pm, msk);
+                    };
                     auto walk = [&](auto reload) {
-                        constexpr bool A = decltype(reload)::value;
-                        step_raw<HC - 1, true>(X, Y, pa[HC - 1] + up, pa[HC - 1] + lw, sel_lo, sel_hi, pm, m3);          // both records (mode 3)
+                        using KA = decltype(reload);
+                        st(std::integral_constant<int, HC - 1>{}, std::true_type{}, X, Y, false);          // both records (mode 3)
                         X2 = X; Y2 = Y;
-                        step_raw<HC, A>(X2, Y2, pa[HC] + up, pa[HC] + lw, sel_lo, sel_hi, pm, m3);
+                        st(std::integral_constant<int, HC>{}, KA{}, X2, Y2, false);
                         emit(HC - 1, X, Y); emit(HC, X2, Y2);
-                        step_raw<HC - 2, A>(Y, X, pa[HC - 2] + lw, pa[HC - 2] + up, sel_lo, sel_hi, pm, m3);             // upwards: roles swapped
-                        step_raw<HC + 1, A>(X2, Y2, pa[HC + 1] + up, pa[HC + 1] + lw, sel_lo, sel_hi, pm, m3);
+                        st(std::integral_constant<int, HC - 2>{}, KA{}, Y, X, true);
+                        st(std::integral_constant<int, HC + 1>{}, KA{}, X2, Y2, false);
                         emit(HC - 2, X, Y); emit(HC + 1, X2, Y2);
                         if constexpr (kTP == 8) {
-                            step_raw<1, A>(Y, X, pa[1] + lw, pa[1] + up, sel_lo, sel_hi, pm, m3);
-                            step_raw<6, A>(X2, Y2, pa[6] + up, pa[6] + lw, sel_lo, sel_hi, pm, m3);
+                            st(std::integral_constant<int, 1>{}, KA{}, Y, X, true);
+                            st(std::integral_constant<int, 6>{}, KA{}, X2, Y2, false);
                             emit(1, X, Y); emit(6, X2, Y2);
-                            step_raw<0, A>(Y, X, pa[0] + lw, pa[0] + up, sel_lo, sel_hi, pm, m3);
-                            step_raw<7, A>(X2, Y2, pa[7] + up, pa[7] + lw, sel_lo, sel_hi, pm, m3);
+                            st(std::integral_constant<int, 0>{}, KA{}, Y, X, true);
+                            st(std::integral_constant<int, 7>{}, KA{}, X2, Y2, false);
                             emit(0, X, Y); emit(7, X2, Y2);
                         }
                     };
