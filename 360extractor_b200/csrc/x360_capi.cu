@@ -156,11 +156,21 @@ bool raw_allowed()
     const char *e = getenv("X360_NO_RAW");
     return !(e && atoi(e));
 }
-bool tiled_raw(bool scores, bool lanczos, int, bool, bool allow) { return allow && !scores && !lanczos; }
+// With the fused score the raw gather measured slower than the planes (cfg4: 228 against 246 Gpix/s — the halo pixel
+// costs 6 loads + 4 PRMT per frame on 96 of a CTA's 128 threads), so it is opt-in there: X360_RAW_SCORES=1.
+bool tiled_raw(bool scores, bool lanczos, int, bool, bool allow)
+{
+    const char *e = getenv("X360_RAW_SCORES");                 // read when a plan is created or previewed
+    return allow && !lanczos && (!scores || (e && atoi(e)));
+}
 
 tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col, bool raw)
 {
-    if (raw) {                          // bilinear, no fused score: selectors per thread (column-only map_x) or per pixel
+    if (raw) {                          // bilinear: selectors per thread (column-only map_x) or per pixel
+        if (scores) {
+            if (th == 16) return col ? extract_tiled<true, false, 4, 4, 6, true, true> : extract_tiled<true, false, 4, 4, 6, true, false>;
+            return col ? extract_tiled<true, false, 8, 4, 5, true, true> : extract_tiled<true, false, 8, 4, 5, true, false>;
+        }
         if (th == 16) return col ? extract_tiled<false, false, 4, 4, 7, true, true> : extract_tiled<false, false, 4, 4, 7, true, false>;
         return col ? extract_tiled<false, false, 8, 4, 7, true, true> : extract_tiled<false, false, 8, 4, X360_MINB8, true, false>;
     }

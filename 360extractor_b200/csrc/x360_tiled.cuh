@@ -127,9 +127,10 @@ template <int TH> struct TGray {
 __host__ __device__ constexpr uint32_t tiled_off_sy(int th) { return kOffTile + (uint32_t)th * kTile * 3; }          // Q5 map_y (< 2^20): 2 byte planes + 1 nibble plane
 __host__ __device__ constexpr uint32_t tiled_off_gray(int th) { return tiled_off_sy(th) + (uint32_t)th * kTile * 5 / 2; }   // 20 bits per value
 // fp64 map_x: a TH x 32 tile, or ONE row of 32 where map_x does not depend on the output row (column-only units)
+__host__ __device__ constexpr uint32_t tiled_gray_bytes(int th) { return ((uint32_t)((th + 2) * kTile + 2 * th) + 127u) & ~127u; }
 __host__ __device__ constexpr uint32_t tiled_off_u0(bool scores, int th)
 {
-    return scores ? ((tiled_off_gray(th) + (uint32_t)((th + 2) * kTile + 2 * th) + 127u) & ~127u) : tiled_off_gray(th);
+    return scores ? tiled_off_gray(th) + tiled_gray_bytes(th) : tiled_off_gray(th);
 }
 __host__ __device__ constexpr uint32_t tiled_u0_bytes(int th, bool col_only) { return col_only ? kTile * 8u : (uint32_t)th * kTile * 8u; }   // column-only: one row (every warp writes the same values)
 __host__ __device__ constexpr uint32_t tiled_off_raw(bool scores, int th, bool col_only) { return tiled_off_u0(scores, th) + tiled_u0_bytes(th, col_only); }
@@ -146,7 +147,9 @@ __host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max, 
 __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th, bool col_only, bool raw = false)
 {
     // RAW: ctrl | packed tile | map_y | map_x row | raw x2 | second packed tile
-    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + kTRawBufs * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3;
+    // (+ with the fused score: second gray tile, second set of per-warp sums — a frame's barrier is shared by both copies)
+    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + kTRawBufs * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3 +
+                    (scores ? tiled_gray_bytes(th) + 128u : 0u);
     // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
     return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
            (lanczos ? (size_t)kTWMax * 32 * 144 : 0);
@@ -452,7 +455,7 @@ template <bool SCORES, bool LZ, int TP, int NW, int MINB = tiled_min_ctas(SCORES
 __global__ void __launch_bounds__(32 * NW, MINB)
 extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ TiledMaps tms)
 {
-    static_assert(!RAW || (!LZ && !SCORES), "the raw gather is bilinear without the fused score");
+    static_assert(!RAW || !LZ, "the raw gather is bilinear");
     extern __shared__ __align__(128) uint8_t dsm[];
     const Geom &g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,7 +473,6 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
     double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(SCORES, TH));
     uint8_t *const sy_s = dsm + tiled_off_sy(TH);                                   // 3 byte planes of TH x 32 values
-    TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + tiled_off_gray(TH));
     const bool col_u0 = a.col_u0 != 0;
     uint32_t kOffRaw = tiled_off_raw(SCORES, TH, col_u0);                           // (a register: two layouts)
     asm volatile("" : "+r"(kOffRaw));
@@ -478,6 +480,8 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     asm volatile("" : "+r"(raw_bytes));                                             // keep in a register (cheaper than rematerialising)
     const uint32_t off_pairs = kOffRaw + (uint32_t)NB * raw_bytes;                  // dsm-relative (RAW: the second packed tile)
     const uint32_t off_hi = off_pairs + tiled_lo_bytes(a.rows_max, a.bw_max);          // bilinear: hi plane after the lo plane
+    const uint32_t off_gray2 = off_pairs + (uint32_t)TH * kTile * 3u;                  // RAW + SCORES: second gray tile, then second per-warp sums
+    const uint32_t off_wsum2 = off_gray2 + tiled_gray_bytes(TH);
     const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max, LZ) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
@@ -648,7 +652,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         const uint32_t o = (uint32_t)delta + 3u * rx;
                         pa[k] = raw_s + ry * bw + (o & ~3u);                            // upper record in raw buffer 0; lower: + bw
                         pa2[k] = 0; ph[k] = 0; ph2[k] = 0;
-                        if constexpr (!COLSEL) {
+                        if (!COLSEL || k == kTP) {
                             const uint32_t al_k = o & 3u;
                             psel[k] = (0x4130u + 0x1111u * al_k) | ((((al_k + 6u) & 7u) | (((al_k + 1u) & 7u) << 4)) << 16) | (al_k == 3u ? 0x80000000u : 0u);
                         }
@@ -749,13 +753,18 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncthreads();                  // pairs ready, raw consumed, tile buffer free
                 }
-                if (SCORES && tid == 0 && f > f_begin) {
-                    long long s1 = 0, s2 = 0;                 // every warp's partial of frame f-1 is in (barrier above)
+                // RAW: gray tile and per-warp sums alternate between two copies like the packed tile (one barrier per frame)
+                TGray<TH> &gt = *reinterpret_cast<TGray<TH> *>(dsm + ((RAW && (it & 1u)) ? off_gray2 : tiled_off_gray(TH)));
+                int (*const wsum)[2] = (RAW && (it & 1u)) ? reinterpret_cast<int (*)[2]>(dsm + off_wsum2) : ctl.wsum;
+                int (*const wsum_prev)[2] = (RAW && !(it & 1u)) ? reinterpret_cast<int (*)[2]>(dsm + off_wsum2) : ctl.wsum;
+                auto flush_prev = [&]() {                     // every warp's partial of frame f-1 is in (a barrier since)
+                    long long s1 = 0, s2 = 0;
 #pragma unroll
-                    for (int w = 0; w < kTW; ++w) { s1 += ctl.wsum[w][0]; s2 += (unsigned)ctl.wsum[w][1]; }
+                    for (int w = 0; w < kTW; ++w) { s1 += wsum_prev[w][0]; s2 += (unsigned)wsum_prev[w][1]; }
                     atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f - 1) * a.V + v], (unsigned long long)s1);
                     atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f - 1) * a.V + v], (unsigned long long)s2);
-                }
+                };
+                if (SCORES && !RAW && tid == 0 && f > f_begin) flush_prev();
                 const uint32_t tile_off = (RAW && (it & 1u)) ? off_pairs : kOffTile;   // RAW: two packed tiles, alternating
                 uint32_t obase = tile_off + my_word;
                 if (!(RAW && staged)) asm volatile("" : "+r"(obase));
@@ -769,6 +778,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         const uint32_t pxl = combine_pairs(U, V, pb[k], pc[k]);
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ot + (uint32_t)(k * kTile * 3)), "r"(__byte_perm(pxl, nb, pack_sel)) : "memory");
+                        if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     };
                     auto st = [&](auto kc, auto ac, uint2 &P, uint2 &Q, bool up_walk) {
                         constexpr int K = decltype(kc)::value;
@@ -798,6 +808,16 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                         }
                     };
                     if (any_a) walk(std::true_type{}); else walk(std::false_type{});
+                    if (SCORES && hvalid) {                                  // the halo pixel: both records, its own selectors
+                        const uint32_t slo = psel[kTP], shi = psel[kTP] >> 16;
+                        const bool a3 = (int)psel[kTP] < 0;
+                        const uint32_t *u = reinterpret_cast<const uint32_t *>(dsm + (pa[kTP] + up - dsm_s));
+                        const uint32_t *l = reinterpret_cast<const uint32_t *>(dsm + (pa[kTP] + lw - dsm_s));
+                        const uint32_t u0 = u[0], u1 = u[1], u2 = a3 ? u[2] : u0, l0 = l[0], l1 = l[1], l2 = a3 ? l[2] : l0;
+                        const uint2 h0 = make_uint2(__byte_perm(u0, u1, slo), __byte_perm(u1, u2, shi));
+                        const uint2 h1 = make_uint2(__byte_perm(l0, l1, slo), __byte_perm(l1, l2, shi));
+                        halo_store_t<TH>(gt, tid, (uint8_t)gray_of(combine_pairs(h0, h1, pb[kTP], pc[kTP])));
+                    }
                   } else if constexpr (LZ) {
 #pragma unroll
                     for (int k = 0; k < kTP; ++k) {
@@ -867,6 +887,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (a.store_ok) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();                      // tile (+ gray halo) complete; pairs / raw rows free for the next frame
                 if constexpr (RAW) ot ^= ot_toggle;
+                if (SCORES && RAW && tid == 0 && f > f_begin) flush_prev();
 
                 if (a.store_ok) {
                     if (tid == 0) {
@@ -893,16 +914,17 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     pl = __reduce_add_sync(0xffffffffu, pl);
                     pl2 = __reduce_add_sync(0xffffffffu, pl2);
                     if (lane == 0) {
-                        ctl.wsum[warp][0] = pl;               // |sum L| <= 1020 * 256, sum L^2 <= 1020^2 * 256 < 2^32
-                        ctl.wsum[warp][1] = (int)pl2;
+                        wsum[warp][0] = pl;                   // |sum L| <= 1020 * 256, sum L^2 <= 1020^2 * 256 < 2^32
+                        wsum[warp][1] = (int)pl2;
                     }
                 }
             }
             __syncthreads();                           // every warp's partial of the last frame is in
             if (SCORES && tid == 0) {
                 long long s1 = 0, s2 = 0;
+                int (*const wsum_last)[2] = (RAW && !(it & 1u)) ? reinterpret_cast<int (*)[2]>(dsm + off_wsum2) : ctl.wsum;   // `it` is past the last frame
 #pragma unroll
-                for (int w = 0; w < kTW; ++w) { s1 += ctl.wsum[w][0]; s2 += (unsigned)ctl.wsum[w][1]; }
+                for (int w = 0; w < kTW; ++w) { s1 += wsum_last[w][0]; s2 += (unsigned)wsum_last[w][1]; }
                 atomicAdd((unsigned long long *)&a.sum_lap[(size_t)(f_end - 1) * a.V + v], (unsigned long long)s1);
                 atomicAdd((unsigned long long *)&a.sum_lap2[(size_t)(f_end - 1) * a.V + v], (unsigned long long)s2);
             }

@@ -149,6 +149,21 @@ def test_raw_gather_ring_plans(x360, oracle, monkeypatch, cfg, no_raw):
         assert modes["staged"] == 0
 
 
+@pytest.mark.parametrize("cfg", [(256, 512, 96, 90, "cube", 6, 0, 3), (192, 384, 80, 60, "ring", 8, -20, 2), (512, 1024, 256, 90, "ring", 8, 0, 5)])
+def test_raw_gather_with_fused_score_opt_in(x360, oracle, monkeypatch, cfg):
+    """X360_RAW_SCORES=1: the raw gather with the fused score (double-buffered gray tile and per-warp sums) — measured slower
+    than the planes on cfg4, so off by default, but kept bit-exact."""
+    H, W, d, fov, layout, n, pitch, F = cfg
+    monkeypatch.setenv("X360_RAW_SCORES", "1")
+    frames = np.stack([noise_frame(500 + i, H, W) for i in range(F)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout))
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, 0)
+    with x360.Extractor(H, W, d, fov, R, "linear", max_batch=F) as ex:
+        got, s, s2 = ex.extract_sums(frames)
+    assert_same(got, want, f"{cfg} raw + scores")
+    assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
+
+
 def test_roll_and_active_camera_subset(x360, oracle):
     views = x360.GeometryProcessor.generate_views(12, 0, "ring")
     names, R = x360.rotation_stack(views, active_cameras=[0, 3, 6, 9])
