@@ -375,6 +375,7 @@ struct x360_plan {
     bool col_u0 = false;                 // map_x depends on the output column only (yaw-only rotations)
     int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with scores
     bool t_raw[2] = {false, false};      // the launch takes the raw-gather variant (no transform)
+    bool split_score = false;            // X360_SPLIT_SCORE=1: scores by a separate pass over the views instead of the fused reduction
     // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
     // coarsest one that still yields enough work items without cutting the frame batch into chunks
     int n_units[4] = {0, 0, 0, 0};
@@ -414,6 +415,23 @@ static int plan_grid(const x360_plan *pl, bool scores)
 static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint8_t *out_views, int64_t *sum_lap,
                         int64_t *sum_lap2, cudaStream_t st)
 {
+    if (sum_lap && pl->split_score) {
+        // experiment (X360_SPLIT_SCORE=1): extraction without the fused score, then one streaming pass over the views
+        if (int rc = launch_tiled(pl, frames, n_frames, out_views, nullptr, nullptr, st)) return rc;
+        const Geom &g = pl->g;
+        const int n = n_frames * pl->p.n_views;
+        CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n, st));
+        CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n, st));
+        const int fast = ((uintptr_t)out_views % 4 == 0) && (g.ow % 4 == 0);
+        for (int n0 = 0; n0 < n; n0 += 32768) {
+            const int m = std::min(32768, n - n0);
+            blur_sums_views_kernel<<<dim3((unsigned)((g.ow + kBsW - 1) / kBsW), (unsigned)((g.oh + kBsH - 1) / kBsH), (unsigned)m), 256, 0, st>>>(
+                out_views + (size_t)n0 * g.oh * g.ow * 3, g.oh, g.ow, fast, (long long *)sum_lap + n0, (long long *)sum_lap2 + n0);
+            g_launches.fetch_add(1);
+        }
+        CU(cudaGetLastError());
+        return X360_OK;
+    }
     const bool scores = sum_lap != nullptr;
     const Geom &g = pl->g;
     TiledArgs a;
@@ -567,6 +585,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         const bool lz = params->interp == X360_INTERP_LANCZOS4;
         pl->col_u0 = column_only_map_x(params->R, params->n_views) && !(getenv("X360_NO_COL_U0") && atoi(getenv("X360_NO_COL_U0")));
         const bool allow_raw = raw_allowed();
+        if (const char *e = getenv("X360_SPLIT_SCORE")) pl->split_score = atoi(e) != 0;
         for (int sc = 0; sc < 2; ++sc) {
             int rows = 40, bw = 144, th = 32;
             choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, allow_raw, &rows, &bw, &th);

@@ -82,6 +82,100 @@ laplacian_sums_kernel(const uint8_t *__restrict__ gray, int h, int w, long long 
     }
 }
 
+// Laplacian sums of a whole batch of views already in device memory: uint8 [n][h][w][3] -> (sum L, sum L^2)[n]
+// (ImageUtils.calculate_blur_score, src/utils/image_utils.py:22-27, for every view of a launch).  The split
+// alternative to the score fused into the extraction kernel: one more pass over the output (3 B / pixel), no halo
+// gathers.  One CTA per 128 x 32 tile: Q15 gray of the tile and its 1-px ring (reflect-101 at the image borders,
+// applied while loading) in shared memory, then the same dp4a Laplacian as the fused path.
+constexpr int kBsW = 128, kBsH = 32, kBsPitch = 136;       // gray tile: column c at byte 4 + c (c = -1 .. 128)
+
+__device__ __forceinline__ int reflect101_clamped(int p, int len)
+{
+    if (p < 0) p = -p;
+    if (p >= len) p = 2 * len - 2 - p;
+    return min(max(p, 0), len - 1);
+}
+
+__global__ void __launch_bounds__(256)
+blur_sums_views_kernel(const uint8_t *__restrict__ views, int h, int w, int fast, long long *__restrict__ sum, long long *__restrict__ sum2)
+{
+    __shared__ __align__(16) uint8_t g[kBsH + 2][kBsPitch];
+    __shared__ int red[8][2];
+    const int tid = threadIdx.x, x0 = blockIdx.x * kBsW, y0 = blockIdx.y * kBsH;
+    const uint8_t *img = views + (size_t)blockIdx.z * h * w * 3;
+    // main part: (kBsH + 2) rows x 32 four-pixel groups, 5 per thread; all loads first (the pass is latency-bound otherwise)
+    constexpr int kIt = ((kBsH + 2) * 32 + 255) / 256;
+    uint32_t wv[kIt][3];
+    bool quick[kIt];
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+        const int i = tid + 256 * k, r = i >> 5, x = x0 + 4 * (i & 31);
+        quick[k] = fast && r < kBsH + 2 && x + 3 < w;
+        if (quick[k]) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(img + ((size_t)reflect101_clamped(y0 - 1 + r, h) * w + x) * 3);
+            wv[k][0] = __ldg(src); wv[k][1] = __ldg(src + 1); wv[k][2] = __ldg(src + 2);   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+        }
+    }
+    if (tid < 2 * (kBsH + 2)) {                                   // the ring's left / right columns
+        const int r = tid >> 1, side = tid & 1;
+        const uint8_t *px = img + ((size_t)reflect101_clamped(y0 - 1 + r, h) * w + reflect101_clamped(side ? x0 + kBsW : x0 - 1, w)) * 3;
+        g[r][side ? 4 + kBsW : 3] = (uint8_t)gray_of((uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16));
+    }
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+        const int i = tid + 256 * k, r = i >> 5, gq = i & 31, x = x0 + 4 * gq;
+        if (r >= kBsH + 2) continue;
+        uint32_t gw;
+        if (quick[k]) {
+            gw = gray_of(wv[k][0]) | (gray_of(__byte_perm(wv[k][0], wv[k][1], 0x0543)) << 8) |
+                 (gray_of(__byte_perm(wv[k][1], wv[k][2], 0x0432)) << 16) | (gray_of(wv[k][2] >> 8) << 24);
+        } else {                                                  // image edge or unaligned rows: pixel by pixel, reflected
+            const uint8_t *row = img + (size_t)reflect101_clamped(y0 - 1 + r, h) * w * 3;
+            gw = 0;
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t *px = row + (size_t)reflect101_clamped(x + j, w) * 3;
+                gw |= gray_of((uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16)) << (8 * j);
+            }
+        }
+        *reinterpret_cast<uint32_t *>(&g[r][4 + 4 * gq]) = gw;
+    }
+    __syncthreads();
+    int pl = 0;
+    unsigned pl2 = 0;
+    const int gq = tid & 31, x = x0 + 4 * gq;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = (tid >> 5) * 4 + rr;
+        if (y0 + r >= h || x >= w) continue;
+        const uint32_t C = *reinterpret_cast<const uint32_t *>(&g[r + 1][4 + 4 * gq]);
+        const uint32_t U = *reinterpret_cast<const uint32_t *>(&g[r][4 + 4 * gq]);
+        const uint32_t D = *reinterpret_cast<const uint32_t *>(&g[r + 2][4 + 4 * gq]);
+        const uint32_t l = g[r + 1][3 + 4 * gq], rg = g[r + 1][8 + 4 * gq];
+        const uint32_t Lw = __byte_perm(C, l, 0x2104);             // [l, c0, c1, c2]
+        const uint32_t Rw = __byte_perm(C, rg, 0x4321);            // [c1, c2, c3, r]
+        constexpr uint32_t kA = 0x0001fc01u;                       // [ 1, -4,  1,  0]
+        constexpr uint32_t kB = 0x01fc0100u;                       // [ 0,  1, -4,  1]
+        int L[4];
+        L[0] = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
+        L[1] = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
+        L[2] = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
+        L[3] = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x + j < w) { pl += L[j]; pl2 += (unsigned)(L[j] * L[j]); }
+    }
+    pl = __reduce_add_sync(0xffffffffu, pl);
+    pl2 = __reduce_add_sync(0xffffffffu, pl2);                    // <= 32 x 16 x 1020^2 < 2^32
+    if ((tid & 31) == 0) { red[tid >> 5][0] = pl; red[tid >> 5][1] = (int)pl2; }
+    __syncthreads();
+    if (tid == 0) {
+        long long s1 = 0, s2 = 0;
+        for (int k = 0; k < 8; ++k) { s1 += red[k][0]; s2 += (unsigned)red[k][1]; }
+        atomicAdd((unsigned long long *)&sum[blockIdx.z], (unsigned long long)s1);
+        atomicAdd((unsigned long long *)&sum2[blockIdx.z], (unsigned long long)s2);
+    }
+}
+
 // hand the views of the selected faces to the masker without leaving the device.
 // src/core/processor.py:392-420 passes the BGR views (all of them, or the faces named in 'ai_mask_cameras') to
 // AIService.process_batch (src/core/ai_model.py:125-167), whose model turns each image into a normalised

@@ -164,6 +164,21 @@ def test_raw_gather_with_fused_score_opt_in(x360, oracle, monkeypatch, cfg):
     assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
 
 
+@pytest.mark.parametrize("cfg", [(256, 512, 96, 90, "cube", 6, 0, 3), (200, 400, 95, 110, "fibonacci", 7, -20, 2), (512, 1024, 260, 90, "ring", 8, 0, 2),
+                                 (128, 256, 33, 100, "ring", 2, -90, 1)])
+def test_split_score_pass_matches_the_fused_one(x360, oracle, monkeypatch, cfg):
+    """X360_SPLIT_SCORE=1: the Laplacian sums from one streaming pass over the finished views instead of the fused reduction."""
+    H, W, d, fov, layout, n, pitch, F = cfg
+    monkeypatch.setenv("X360_SPLIT_SCORE", "1")
+    frames = np.stack([noise_frame(600 + i, H, W) for i in range(F)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout))
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, 0)
+    with x360.Extractor(H, W, d, fov, R, "linear", max_batch=F) as ex:
+        got, s, s2 = ex.extract_sums(frames)
+    assert_same(got, want, f"{cfg} split score")
+    assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
+
+
 def test_roll_and_active_camera_subset(x360, oracle):
     views = x360.GeometryProcessor.generate_views(12, 0, "ring")
     names, R = x360.rotation_stack(views, active_cameras=[0, 3, 6, 9])
