@@ -2,7 +2,7 @@
 //
 // Contract: src/core/processor.py:327-342 for a frame batch — cv2.remap(INTER_LINEAR | INTER_LANCZOS4,
 // BORDER_WRAP) and, optionally, calculate_blur_score — with the map of src/core/geometry.py:141-190
-// evaluated on the fly and never stored in HBM.  extract_tiled<SCORES, LZ, TP, NW>:
+// evaluated on the fly and never stored in HBM.  extract_tiled<SCORES, LZ, TP, NW, MINB, RAW, COLSEL>:
 //
 //   work item   = (view unit, 32 x (NW TP) output tile, frame chunk), handed out by a global atomic
 //                 counter.  A view unit is a set of views whose rotations differ only by a yaw (ring
@@ -26,6 +26,10 @@
 //                 4. pack: one SHFL + one PRMT turn four lanes' pixels into three BGR words, STS.32
 //                    into the packed tile, which leaves by ONE TMA store (UTMASTG) per tile and frame;
 //                 5. SCORES: gray tile + 1-px halo, dp4a Laplacian, integer sums (image_utils.py:22-27).
+//   RAW (bilinear plans without the fused score, the default there): steps 2-3 collapse — no transform, no
+//                 record planes; the gather reads the packed BGR bytes of the TMA box itself (2-3 LDS.32 + LOP3
+//                 + 2 PRMT rebuild the pair record in registers, step_raw), three raw buffers (the box of frame
+//                 f + 3 flies during frame f), two packed tiles alternating per frame, ONE barrier per frame.
 //
 // Exactness of the u16 weights: w*64 <= 65535 except w00 = 1024 (fx = fy = 0, all other weights
 // 0), which is clamped to 65535: (65535 s + 32768) >> 16 = s for every byte s.  Everything else
@@ -146,7 +150,7 @@ __host__ __device__ inline uint32_t tiled_pairs_bytes(int rows_max, int bw_max, 
 }
 __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, bool scores, bool lanczos, int th, bool col_only, bool raw = false)
 {
-    // RAW: ctrl | packed tile | map_y | map_x row | raw x2 | second packed tile
+    // RAW: ctrl | packed tile | map_y | [gray] | map_x | raw x3 | second packed tile | [second gray tile | second per-warp sums]
     // (+ with the fused score: second gray tile, second set of per-warp sums — a frame's barrier is shared by both copies)
     if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + kTRawBufs * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3 +
                     (scores ? tiled_gray_bytes(th) + 128u : 0u);
@@ -472,7 +476,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
     double *const u0s = reinterpret_cast<double *>(dsm + tiled_off_u0(SCORES, TH));
-    uint8_t *const sy_s = dsm + tiled_off_sy(TH);                                   // 3 byte planes of TH x 32 values
+    uint8_t *const sy_s = dsm + tiled_off_sy(TH);                                   // 20-bit values: 2 byte planes + 1 nibble plane of TH x 32
     const bool col_u0 = a.col_u0 != 0;
     uint32_t kOffRaw = tiled_off_raw(SCORES, TH, col_u0);                           // (a register: two layouts)
     asm volatile("" : "+r"(kOffRaw));
