@@ -243,13 +243,27 @@ struct HostUnits {
     std::vector<double> shift;
 };
 
-HostUnits build_units(const double *R, int V, int W, bool share, int max_views = kTMaxUnitViews)
+// Does an output pixel of this view look (within 1e-3 px) straight at a pole?  There v0 and v2 are rounding residues
+// (~1e-16) and map_x = atan2(v0, v2) is decided by each view's own residues (geometry.py:158-172), so the identity
+// "map_x of a yaw-shifted view = map_x of the first view + shift" does not hold bit for bit: such views keep a unit of
+// their own and evaluate their own map.  (The pole direction in camera coordinates is +-(R10, R11, R12).)
+bool has_pole_pixel(const double *Rv, const Geom &g)
+{
+    if (std::fabs(Rv[5]) < 1e-12) return false;                           // poles on the horizon of the image plane
+    const double px = g.cx + g.f * (Rv[3] / Rv[5]), py = g.cy + g.f * (Rv[4] / Rv[5]);
+    const double rx = std::nearbyint(px), ry = std::nearbyint(py);
+    return std::fabs(px - rx) < 1e-3 && std::fabs(py - ry) < 1e-3 && rx >= 0.0 && rx < (double)g.ow && ry >= 0.0 && ry < (double)g.oh;
+}
+
+HostUnits build_units(const double *R, int V, int W, const Geom &g, bool share, int max_views = kTMaxUnitViews)
 {
     std::vector<std::vector<int>> members;
     std::vector<std::vector<double>> shifts;
     for (int v = 0; v < V; ++v) {
         bool placed = false;
-        for (size_t u = 0; share && u < members.size() && !placed; ++u) {
+        const bool alone = has_pole_pixel(R + 9 * v, g);
+        for (size_t u = 0; share && !alone && u < members.size() && !placed; ++u) {
+            if (has_pole_pixel(R + 9 * members[u][0], g)) continue;
             double d;
             if ((int)members[u].size() < max_views && yaw_delta(R + 9 * members[u][0], R + 9 * v, &d)) {
                 double sh = d / (2.0 * 3.14159265358979323846) * (double)W;
@@ -531,7 +545,8 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
     if (params->struct_size != (int32_t)sizeof(x360_params)) return fail(X360_E_INVALID, "x360_params.struct_size mismatch");
     if (int rc = check_dims(params->src_w, params->src_h, params->out_w, params->out_h)) return rc;
     if (!(params->fov_deg > 0.0 && params->fov_deg < 180.0)) return fail(X360_E_INVALID, "fov_deg %g outside (0, 180)", params->fov_deg);
-    const HostUnits h = build_units(params->R, params->n_views, params->src_w, true);
+    const HostUnits h = build_units(params->R, params->n_views, params->src_w,
+                                    make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), true);
     if (n_units) *n_units = (int32_t)h.units.size();
     for (size_t u = 0; u < h.units.size(); ++u)
         for (int i = 0; i < h.units[u].n; ++i) {
@@ -639,7 +654,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (e == cudaSuccess && pl->path == X360_PATH_TILED) {
         const bool share = !(getenv("X360_NO_SHARE") && atoi(getenv("X360_NO_SHARE")));
         for (int lv = 0; lv < 4 && e == cudaSuccess; ++lv) {
-            const HostUnits h = build_units(params->R, params->n_views, params->src_w, share, kTMaxUnitViews >> lv);
+            const HostUnits h = build_units(params->R, params->n_views, params->src_w, pl->g, share, kTMaxUnitViews >> lv);
             pl->n_units[lv] = (int)h.units.size();
             e = cudaMalloc(&pl->d_units[lv], sizeof(TiledUnit) * h.units.size());
             if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_view[lv], sizeof(int) * h.view.size());

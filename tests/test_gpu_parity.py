@@ -179,6 +179,26 @@ def test_split_score_pass_matches_the_fused_one(x360, oracle, monkeypatch, cfg):
     assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
 
 
+@pytest.mark.parametrize("cfg", [(510, 1020, 228, 90.0, 10, 45, True), (97, 972, 70, 80.0, 11, 50, True), (256, 512, 128, 90.0, 8, 45, False),
+                                 (256, 512, 96, 60.0, 6, 60, False)])
+def test_views_with_a_pixel_on_the_pole_do_not_share_a_map(x360, oracle, cfg):
+    """pitch + fov / 2 = 90 deg and an even output size: the top (bottom) centre pixel looks exactly at a pole, where map_x is
+    decided by each view's own rounding residues (found by scripts/fuzz_parity.py).  Such views evaluate their own map."""
+    H, W, d, fov, n, pitch, scores = cfg
+    frames = np.stack([noise_frame(800 + i, H, W) for i in range(3)])
+    views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode="ring")
+    R = rotations(x360, views)[:8]
+    assert x360.plan_preview(H, W, d, fov, R)["n_units"] == len(R)
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, 0, want_scores=scores)
+    with x360.Extractor(H, W, d, fov, R, "linear", max_batch=3) as ex:
+        if scores:
+            got, s, s2 = ex.extract_sums(frames)
+            assert np.array_equal(s, ws) and np.array_equal(s2, ws2)
+        else:
+            got, _ = ex.extract(frames, want_scores=False)
+    assert_same(got, want, f"{cfg} pole pixel")
+
+
 def test_roll_and_active_camera_subset(x360, oracle):
     views = x360.GeometryProcessor.generate_views(12, 0, "ring")
     names, R = x360.rotation_stack(views, active_cameras=[0, 3, 6, 9])

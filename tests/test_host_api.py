@@ -223,6 +223,15 @@ def test_plan_preview_view_units(x360):
     assert all(0.0 <= s < 5760 for s in pv["shift_px"])
 
 
+def test_plan_preview_pole_pixel_views_stay_alone(x360):
+    # pitch 45 + fov 90 / 2 = 90 deg, even d: pixel (d / 2, 0) of every view looks straight at the pole -> no map sharing
+    views = x360.GeometryProcessor.generate_views(8, 45, "ring")
+    R = x360.rotation_stack(views)[1]
+    assert x360.plan_preview(512, 1024, 228, 90, R)["n_units"] == 8
+    assert x360.plan_preview(512, 1024, 229, 90, R)["n_units"] == 1           # odd d: the pole falls between pixels
+    assert x360.plan_preview(512, 1024, 228, 80, R)["n_units"] == 1           # pole outside the view
+
+
 def test_plan_preview_capacity(x360):
     views = x360.GeometryProcessor.generate_views(8, 0, "ring")
     pv = x360.plan_preview(2880, 5760, 1600, 90, x360.rotation_stack(views)[1])
