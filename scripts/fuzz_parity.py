@@ -25,6 +25,9 @@ for c in range(n_cases):
     layout = str(rng.choice(["ring", "ring", "cube", "fibonacci"]))
     n = int(rng.integers(1, 13))
     pitch = int(rng.choice([0, 0, 0, -20, 20, 45, -45, -90, int(rng.integers(-90, 91))]))
+    if rng.random() < 0.15:                            # a view edge or centre exactly on a pole / the horizon
+        pitch = int(rng.choice([90 - fov / 2, fov / 2 - 90, 90, -90, fov / 2, -fov / 2]))
+        d += d & 1                                     # even size: pixel (d / 2, 0) lies on the optical axis' column
     F = int(rng.integers(1, 8))
     interp = 1 if rng.random() < 0.2 else 0
     scores = bool(rng.random() < 0.4)
