@@ -12,6 +12,7 @@ X360_OK = 0
 INTERP_LINEAR = 0
 INTERP_LANCZOS4 = 1
 PATH_AUTO, PATH_DIRECT, PATH_STAGED, PATH_TILED = 0, 1, 2, 3
+FLAG_PLANES, FLAG_FUSED_SCORE, FLAG_SPLIT_SCORE, FLAG_TILE_H16, FLAG_TILE_H32, FLAG_NO_WIDE = 1, 2, 4, 8, 16, 32
 
 
 class X360Error(RuntimeError):
@@ -34,7 +35,7 @@ class Params(ctypes.Structure):
         ("device", ctypes.c_int32),
         ("max_batch", ctypes.c_int32),
         ("path", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
 
 

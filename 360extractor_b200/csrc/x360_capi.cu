@@ -31,6 +31,8 @@ using namespace x360;
 
 namespace {
 
+constexpr int kRingSlots = 64, kRingWords = 8;
+
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 
@@ -51,6 +53,20 @@ int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess)                                                                   \
             return fail(X360_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// Tuning switches for experiments exist only in libraries built with -DX360_LAB; the default build reads no
+// environment variable (plan variants are chosen by the plan, or by x360_params.flags).
+#ifdef X360_LAB
+inline const char *lab_env(const char *name) { return getenv(name); }
+#else
+inline const char *lab_env(const char *) { return nullptr; }
+#endif
+inline int lab_int(const char *name, int dflt) { const char *e = lab_env(name); return e ? atoi(e) : dflt; }
+
+// Dynamic shared memory the tiled kernels may be given (choose_capacity never exceeds it).  The limit is a property of
+// the kernel FUNCTION, shared by every plan of the process, so it is always raised to this one cap — never to a plan's
+// own size, which would lower it under another live plan.
+constexpr int kTiledSmemCap = 110 * 1024;
 
 // geometry.py:141 — f = (0.5*dest_w) / tan(0.5*radians(fov_deg)); radians(x) = x*(pi/180)
 double focal_of(int out_w, double fov_deg)
@@ -80,6 +96,7 @@ int check_dims(int W, int H, int ow, int oh)
     return X360_OK;
 }
 
+#ifdef X360_LAB     // the round-1 comparison kernels (x360_params.path 1 / 2)
 typedef void (*extract_fn)(const ExtractArgs);
 typedef void (*staged_fn)(const ExtractArgs, const TmapSet);
 
@@ -98,10 +115,11 @@ extract_fn pick_direct(int interp, bool scores)
 // occupancy for instruction-level parallelism inside the gather.
 staged_fn pick_staged(bool scores)
 {
-    static const int minb = [] { const char *e = getenv("X360_STAGED_MINB"); return e ? atoi(e) : 4; }();
+    static const int minb = lab_int("X360_STAGED_MINB", 4);
     if (minb == 3) return scores ? extract_linear_staged<true, 3> : extract_linear_staged<false, 3>;
     return scores ? extract_linear_staged<true, 4> : extract_linear_staged<false, 4>;
 }
+#endif
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked).
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -121,6 +139,7 @@ encode_tiled_fn tensor_map_encoder()
     return fn;
 }
 
+#ifdef X360_LAB
 // uint8 [F][H][3W] frame tensor, boxes {128 + 32 k bytes, kBoxRows rows, 1 frame}
 bool encode_frame_maps(const uint8_t *frames, int F, int H, int W, TmapSet *out)
 {
@@ -138,6 +157,7 @@ bool encode_frame_maps(const uint8_t *frames, int F, int H, int W, TmapSet *out)
     }
     return true;
 }
+#endif
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -148,20 +168,34 @@ typedef void (*tiled_fn)(const TiledArgs, const TiledMaps);
 // CTAs, was measured too: equal on cfg2, 20-25 % slower where footprints are large — half the warps per SM.)
 int tiled_warps(bool, int) { return 4; }
 
-// The raw gather (no transform, x360_tiled.cuh RAW) serves the bilinear plans without a fused score.
-// X360_NO_RAW=1 keeps them on the pair-record planes.
-// (The variable is read when a plan is created or previewed; the plan remembers the answer.)
-bool raw_allowed()
+// What a plan may be told instead of choosing by itself: x360_params.flags (include/x360.h), plus — in -DX360_LAB
+// builds only — the environment switches the round-1 experiments used.
+struct PlanOpts {
+    bool planes = false;        // bilinear on the pair-record planes instead of the raw gather
+    int score_mode = 0;         // 0 = the plan's default, 1 = fused into the extraction kernel, 2 = split pass over the views
+    int force_th = 0;           // 16 / 32: output tile height
+    bool no_wide = false;       // no wide / seam boxes
+};
+PlanOpts plan_opts(int flags)
 {
-    const char *e = getenv("X360_NO_RAW");
-    return !(e && atoi(e));
+    PlanOpts o;
+    o.planes = (flags & X360_FLAG_PLANES) != 0 || lab_int("X360_NO_RAW", 0) != 0;
+    o.score_mode = (flags & X360_FLAG_SPLIT_SCORE) ? 2 : ((flags & X360_FLAG_FUSED_SCORE) ? 1 : 0);
+    if (lab_int("X360_SPLIT_SCORE", 0)) o.score_mode = 2;
+    if (lab_int("X360_RAW_SCORES", 0)) o.score_mode = 1;
+    o.force_th = (flags & X360_FLAG_TILE_H16) ? 16 : ((flags & X360_FLAG_TILE_H32) ? 32 : lab_int("X360_TILED_TH", 0));
+    o.no_wide = (flags & X360_FLAG_NO_WIDE) != 0 || lab_int("X360_NO_WIDE", 0) != 0;
+    return o;
 }
-// With the fused score the raw gather measured slower than the planes (cfg4: 228 against 246 Gpix/s — the halo pixel
-// costs 6 loads + 4 PRMT per frame on 96 of a CTA's 128 threads), so it is opt-in there: X360_RAW_SCORES=1.
-bool tiled_raw(bool scores, bool lanczos, int, bool, bool allow)
+// Score policy.  The fused score (gray tile + 1-px halo inside the extraction kernel) is what a plan runs unless told
+// otherwise; with X360_FLAG_PLANES it rides on the pair-record planes, else on the raw gather.
+bool score_is_split(const PlanOpts &o) { return o.score_mode == 2; }
+// The raw gather (no transform, x360_tiled.cuh RAW) serves every bilinear launch except the ones forced onto the
+// planes; by default the fused score still rides on the planes (measured faster in round 1: cfg4 246 vs 228 Gpix/s).
+bool tiled_raw(bool scores, bool lanczos, const PlanOpts &o)
 {
-    const char *e = getenv("X360_RAW_SCORES");                 // read when a plan is created or previewed
-    return allow && !lanczos && (!scores || (e && atoi(e)));
+    if (lanczos || o.planes) return false;
+    return !scores || o.score_mode == 1;
 }
 
 #ifndef X360_RAW_MINB
@@ -186,37 +220,77 @@ tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col, bool raw)
     return scores ? extract_tiled<true, false, 8, 4> : extract_tiled<false, false, 8, 4>;
 }
 
-// load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W];
-// store box {96, 32, 1} of uint8 [F*V][oh][3 ow]
+// load boxes {48 (w + 1) bytes, rows_max - 8 (2 - h) rows, 1 frame} of uint8 [F][H][3W] (raw gather: 64 (w + 1));
+// wide boxes {tiled_wide_bw(c) bytes, wide_rows[c]} through a uint32 view; seam boxes over the window tensor (x360_tiled.cuh);
+// store box {96, tile height, 1} of uint8 [F*V][oh][3 ow].  *wide_ok / *seam_ok report what could be encoded.
 bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max, bool with_in, uint8_t *out, int FV, int oh,
-                       int ow, int tile_h, bool with_out, TiledMaps *tm, bool raw = false)
+                       int ow, int tile_h, bool with_out, TiledMaps *tm, bool raw, const int *wide_rows, bool *wide_ok, bool *seam_ok)
 {
     encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint32_t estr[3] = {1, 1, 1};
+    auto put = [&](CUtensorMap *m, CUtensorMapDataType dt, void *base, const cuuint64_t *dims, const cuuint64_t *strides, cuuint32_t bx,
+                   cuuint32_t by, CUtensorMapL2promotion l2) {
+        const cuuint32_t box[3] = {bx, by, 1};
+        return enc(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
     if (with_in) {
         const cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)F};
         const cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * H};
         for (int k = 0; k < kTNumBox; ++k) {
             const int rows = rows_max - kTBoxRows * (kTNumBoxH - 1 - k / kTNumBoxW);
             const int wk = k % kTNumBoxW;
-            const cuuint32_t box[3] = {(cuuint32_t)(raw ? 64 * (std::min(wk, 3) + 1) : 48 * (wk + 1)), (cuuint32_t)(rows < 8 ? 8 : rows), 1};
-            if (enc(&tm->in[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)frames, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            if (!put(&tm->m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, (void *)frames, dims, strides, (cuuint32_t)(raw ? 64 * (std::min(wk, 3) + 1) : 48 * (wk + 1)),
+                     (cuuint32_t)(rows < 8 ? 8 : rows), CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
                 return false;
         }
+        // wide classes: uint32 elements (a box dimension holds at most 256 elements)
+        if (*wide_ok) {
+            const cuuint64_t d4[3] = {(cuuint64_t)W * 3 / 4, (cuuint64_t)H, (cuuint64_t)F};
+            for (int c = 0; c < kTNumWide && *wide_ok; ++c)
+                if (wide_rows[c] >= 1 &&
+                    !put(&tm->m[kTMapWide0 + c], CU_TENSOR_MAP_DATA_TYPE_UINT32, (void *)frames, d4, strides, (cuuint32_t)(tiled_wide_bw(c) / 4),
+                         (cuuint32_t)wide_rows[c], CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+                    *wide_ok = false;
+        }
+        // seam window: row r = the last kTSeamHalf bytes of global row r and the first kTSeamHalf bytes of row r + 1
+        if (*seam_ok) {
+            const cuuint64_t n_rows = (cuuint64_t)F * H - 1;
+            const cuuint64_t d1[3] = {(cuuint64_t)2 * kTSeamHalf, n_rows, 1}, d4[3] = {(cuuint64_t)2 * kTSeamHalf / 4, n_rows, 1};
+            const cuuint64_t st[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * n_rows};
+            void *base = (void *)(frames + (size_t)W * 3 - kTSeamHalf);
+            for (int w = 0; w < 4 && *seam_ok; ++w)
+                if (!put(&tm->m[kTMapSeam0 + w], CU_TENSOR_MAP_DATA_TYPE_UINT8, base, d1, st, (cuuint32_t)(64 * (w + 1)), (cuuint32_t)(rows_max < 8 ? 8 : rows_max),
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+                    *seam_ok = false;
+            for (int c = 0; c < kTNumWide && *seam_ok && *wide_ok; ++c)
+                if (wide_rows[c] >= 1 &&
+                    !put(&tm->m[kTMapSeam0 + 4 + c], CU_TENSOR_MAP_DATA_TYPE_UINT32, base, d4, st, (cuuint32_t)(tiled_wide_bw(c) / 4), (cuuint32_t)wide_rows[c],
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+                    *seam_ok = false;
+        }
+    } else {
+        *wide_ok = false;
+        *seam_ok = false;
     }
     if (with_out) {
         const cuuint64_t dims[3] = {(cuuint64_t)ow * 3, (cuuint64_t)oh, (cuuint64_t)FV};
         const cuuint64_t strides[2] = {(cuuint64_t)ow * 3, (cuuint64_t)ow * 3 * oh};
-        const cuuint32_t box[3] = {(cuuint32_t)(kTile * 3), (cuuint32_t)tile_h, 1};
-        if (enc(&tm->out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)out, dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (!put(&tm->m[kTMapOut], CU_TENSOR_MAP_DATA_TYPE_UINT8, (void *)out, dims, strides, (cuuint32_t)(kTile * 3), (cuuint32_t)tile_h, CU_TENSOR_MAP_L2_PROMOTION_NONE))
             return false;
     }
     return true;
+}
+
+// box heights of the wide classes for a raw buffer of rows_max x bw_max bytes
+void wide_class_rows(int rows_max, int bw_max, int *wide_rows)
+{
+    const int raw = rows_max * bw_max;                            // (not rounded up: the pair-record area is sized from this product)
+    for (int c = 0; c < kTNumWide; ++c) {
+        int r = raw / tiled_wide_bw(c);
+        wide_rows[c] = r > 256 ? 256 : (r >= 6 ? r : 0);          // a class with fewer than 6 rows serves nothing
+    }
 }
 
 // Rb = Ry(delta) Ra ?  (the reference's Ry, geometry.py:105-109) -> delta in radians.
@@ -313,20 +387,21 @@ bool column_only_map_x(const double *R, int V)
     return V > 0;
 }
 
-void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, bool allow_raw, int *rows_out, int *bw_out, int *tile_h_out)
+void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, const PlanOpts &opts, int *rows_out, int *bw_out, int *tile_h_out,
+                     long long *unfit_out = nullptr)
 {
+    long long best_unfit = 0;
     const bool col = column_only_map_x(R, V);
     // measured on cfg2 (B200): 4 CTAs/SM 0.92, 5 CTAs 1.0, 6 CTAs 1.10; fewer CTAs hide less latency
     static const double occ_factor[9] = {0.0, 0.35, 0.6, 0.8, 0.92, 1.0, 1.10, 1.14, 1.17};
     double best = -1.0;
     int best_rows = 40, best_bw = 144, best_th = 32;
     const int m = lanczos ? 7 : 0;                                        // 8x8 taps: 3 before, 4 after
-    int forced_th = 0;
-    if (const char *e = getenv("X360_TILED_TH")) forced_th = atoi(e);
+    const bool raw = tiled_raw(scores, lanczos, opts);
+    struct Foot { int rows, need; bool seam; };
     for (int th = 32; th >= 16; th -= 16) {
-        if (forced_th && forced_th != th) continue;
-        const bool raw = tiled_raw(scores, lanczos, th, col, allow_raw);
-        std::vector<int> rows, bws;
+        if (opts.force_th && opts.force_th != th) continue;
+        std::vector<Foot> feet;
         size_t total = 0;
         const int tiles_y = (g.oh + th - 1) / th;
         for (int v = 0; v < V; ++v) {
@@ -334,7 +409,7 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
             for (int ty = 0; ty < tiles_y; ++ty)
                 for (int tx = 0; tx < g.tiles_x; ++tx) {
                     ++total;
-                    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+                    int xs[9], ymin = INT_MAX, ymax = INT_MIN;
                     for (int j = 0; j < 3; ++j)
                         for (int i = 0; i < 3; ++i) {
                             const int hl = scores ? 1 : 0;                        // halo
@@ -345,35 +420,56 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
                                          v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
                             const double u = (std::atan2(v0, v2) / (2.0 * 3.14159265358979323846) + 0.5) * g.W;
                             const double w = (std::asin(v1 / std::sqrt(v0 * v0 + v1 * v1 + v2 * v2)) / 3.14159265358979323846 + 0.5) * g.H;
-                            const int ix = (int)std::floor(u), iy = (int)std::floor(w);
-                            xmin = std::min(xmin, ix); xmax = std::max(xmax, ix);
+                            xs[3 * j + i] = (int)std::floor(u);
+                            const int iy = (int)std::floor(w);
                             ymin = std::min(ymin, iy); ymax = std::max(ymax, iy);
                         }
-                    if (xmax - xmin > g.W / 2) continue;                  // wraps the seam: never staged
-                    rows.push_back(ymax - ymin + 3 + m);
+                    int xmin = *std::min_element(xs, xs + 9), xmax = *std::max_element(xs, xs + 9);
+                    bool seam = false;
+                    if (xmax - xmin > g.W / 2 || xmax + 1 + (lanczos ? 3 : 0) > g.W - 1) {   // across the seam: unwrapped columns (raw gather only)
+                        if (!raw || opts.no_wide) continue;
+                        for (int &x : xs) x += (x < g.W / 2) ? g.W : 0;
+                        xmin = *std::min_element(xs, xs + 9); xmax = *std::max_element(xs, xs + 9);
+                        seam = true;
+                    }
+                    if (ymin - (lanczos ? 3 : 0) < (seam ? 1 : 0) || ymax + 1 + (lanczos ? 4 : 0) > g.H - 1 - (seam ? 1 : 0)) continue;   // touches a pole row
+                    Foot ft;
+                    ft.rows = ymax - ymin + 3 + m + (seam ? 1 : 0);
                     const int npx = xmax - (xmin & ~3) + 2 + m;
-                    if (raw) bws.push_back((15 + 3 * (xmax - xmin + 3) + 63) / 64 * 64);   // x_org = xmin, worst alignment
-                    else bws.push_back((12 + 3 * (npx + 1) + 47) / 48 * 48);    // worst alignment
+                    ft.need = raw ? 15 + 3 * (xmax - xmin + 3) + (seam ? 8 : 0) : 12 + 3 * (npx + 1);   // worst alignment
+                    ft.seam = seam;
+                    feet.push_back(ft);
                 }
         }
         // 16-row tiles pay the per-frame overheads over half the pixels and reuse fewer records (cfg2: 0.89 at equal CTAs/SM)
         const double th_factor = th == 32 ? 1.0 : 0.93;
-        for (int bw = raw ? 128 : 96; bw <= (raw ? 256 : 48 * kTNumBoxW); bw += raw ? 64 : 48)
+        const int unit = raw ? 64 : 48;
+        for (int bw = raw ? 128 : 96; bw <= (raw ? 256 : 48 * kTNumBoxW); bw += unit)
             for (int r = 24; r <= 96; r += kTBoxRows) {
                 const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th, col, raw) + 1024;
-                if (smem > 110 * 1024) continue;
+                if (smem > (size_t)kTiledSmemCap) continue;
                 int occ = (int)((227 * 1024) / smem);
                 occ = occ > 8 ? 8 : occ;
-                size_t fit = 0;
-                for (size_t i = 0; i < rows.size(); ++i) fit += (rows[i] <= r && bws[i] <= bw);
-                const double cover = total ? (double)fit / (double)total : 0.0;
-                const double score = th_factor * occ_factor[occ] / (cover + 3.0 * (1.0 - cover));
-                if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; best_th = th; }
+                int wr[kTNumWide];
+                wide_class_rows(r, bw, wr);
+                size_t fit = 0, fit_wide = 0;
+                for (const Foot &ft : feet) {
+                    if (ft.rows <= r && (ft.need + unit - 1) / unit * unit <= bw) { ++fit; continue; }
+                    if (opts.no_wide) continue;
+                    for (int c = 0; c < kTNumWide; ++c)
+                        if (ft.need <= tiled_wide_bw(c) && ft.rows <= wr[c]) { ++fit_wide; break; }
+                }
+                // cost per tile: 1 in a regular box, ~1.5 in a wide one (a larger box per pixel), 3 through the direct gathers
+                const double n = (double)(total ? total : 1);
+                const double cost = ((double)fit + 1.5 * (double)fit_wide + 3.0 * (double)(total - fit - fit_wide)) / n;
+                const double score = th_factor * occ_factor[occ] / cost;
+                if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; best_th = th; best_unfit = (long long)(total - fit - fit_wide); }
             }
     }
     *rows_out = best_rows;
     *bw_out = best_bw;
     *tile_h_out = best_th;
+    if (unfit_out) *unfit_out = best_unfit;
 }
 
 }  // namespace
@@ -387,12 +483,33 @@ struct x360_plan {
     int path = X360_PATH_DIRECT;        // resolved path of the extraction kernel
     int px_max = 0, rows_max = 0, pp = 0, raw_pitch = 0;
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
-    unsigned *d_modes = nullptr;         // [3] tile-mode counters of the last launch (+ [3]: tiled work counter)
+    // Per-launch device scratch: a ring of kRingSlots x 8 words — [0..4] tile-mode counters, [5] the dynamic scheduler's
+    // work-item counter — so launches in flight on different streams never share a counter.
+    unsigned *d_modes = nullptr;
+    int ring_next = 0, ring_last = 0;
+    PlanOpts opts;
+    int grid_cap[2] = {0, 0};            // SMs x resident CTAs of the tiled kernel without / with scores (occupancy query at creation)
+    int wide_rows[2][kTNumWide] = {};
+    // tensor maps of the last (frames, batch, out) buffer triple per variant: re-encoded only when a pointer changes
+    struct MapCache {
+        const void *frames = nullptr; const void *out = nullptr; int n_frames = 0;
+        int stage_ok = 0, store_ok = 0; bool wide_ok = false, seam_ok = false;
+        TiledMaps tms;
+    } maps[2], maps2[2];
+    // second launch (x360_tiled.cuh, TiledArgs::mode): larger staging buffers for the (tile, view) pairs the first launch defers
+    bool two_launch[2] = {false, false};
+    int t2_rows[2] = {0, 0}, t2_bw[2] = {0, 0}, wide_rows2[2][kTNumWide] = {}, grid_cap2[2] = {0, 0};
+    size_t t2_smem[2] = {0, 0};
+    static constexpr int kDeferBufs = 4;
+    unsigned *d_defer[kDeferBufs] = {};  // [2 defer_cap] entries + [1] count each
+    cudaEvent_t defer_ev[kDeferBufs] = {};
+    bool defer_used[kDeferBufs] = {};
+    int defer_cap = 0, defer_next = 0;
     // tiled path
     bool col_u0 = false;                 // map_x depends on the output column only (yaw-only rotations)
     int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with scores
     bool t_raw[2] = {false, false};      // the launch takes the raw-gather variant (no transform)
-    bool split_score = false;            // X360_SPLIT_SCORE=1: scores by a separate pass over the views instead of the fused reduction
+    bool split_score = false;            // scores by a separate pass over the finished views instead of the fused reduction
     // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
     // coarsest one that still yields enough work items without cutting the frame batch into chunks
     int n_units[4] = {0, 0, 0, 0};
@@ -411,15 +528,23 @@ struct x360_plan {
     bool pipe_ready = false;
 };
 
-static int plan_grid(const x360_plan *pl, bool scores)
+static int tiled_occupancy(const x360_plan *pl, int sc, size_t smem)
 {
     int occ = 0;
+    const bool lz = pl->p.interp == X360_INTERP_LANCZOS4;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(sc != 0, lz, pl->t_th[sc], pl->col_u0, pl->t_raw[sc]),
+                                                                        32 * tiled_warps(sc != 0, pl->t_th[sc]), smem);
+    if (e != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    return occ;
+}
+
+static int plan_grid(const x360_plan *pl, bool scores)
+{
+    if (pl->path == X360_PATH_TILED) return pl->grid_cap[scores && !pl->split_score ? 1 : 0];   // capped by the item count at launch
+#ifdef X360_LAB
+    int occ = 0;
     cudaError_t e;
-    if (pl->path == X360_PATH_TILED) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, pl->t_th[scores ? 1 : 0], pl->col_u0, pl->t_raw[scores ? 1 : 0]), 32 * tiled_warps(scores, pl->t_th[scores ? 1 : 0]), pl->t_smem[scores ? 1 : 0]);
-        if (e != cudaSuccess || occ < 1) occ = 1;
-        return pl->sm_count * occ;                 // capped by the item count at launch
-    } else if (pl->path == X360_PATH_STAGED)
+    if (pl->path == X360_PATH_STAGED)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_staged(scores), kThreads, pl->smem);
     else
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_direct(pl->p.interp, scores), kThreads, 0);
@@ -427,27 +552,46 @@ static int plan_grid(const x360_plan *pl, bool scores)
     const int n_tiles = pl->p.n_views * pl->g.tiles_x * pl->g.tiles_y;
     const int cap = pl->sm_count * occ;
     return n_tiles < cap ? n_tiles : cap;
+#else
+    return 0;
+#endif
 }
+
+// Tensor maps of a (frames, batch size, out) triple at one staging capacity: encoded when the triple changes and kept
+// (the pipelined host path alternates between two triples; a device-resident caller usually has one).
+static const x360_plan::MapCache *tiled_maps(x360_plan *pl, x360_plan::MapCache &mc, const uint8_t *frames, int n_frames, uint8_t *out_views, int sc,
+                                             int t_rows, const int *wide_rows)
+{
+    if (mc.frames == frames && mc.out == out_views && mc.n_frames == n_frames) return &mc;
+    const Geom &g = pl->g;
+    const int t_th = pl->t_th[sc];
+    mc.frames = nullptr;                               // invalid until the encode below has succeeded
+    mc.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= t_rows && g.W * 3 >= 256;
+    mc.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= t_th;
+    if (lab_int("X360_NO_TMA_STORE", 0)) mc.store_ok = 0;
+    mc.wide_ok = mc.stage_ok && !pl->opts.no_wide;
+    mc.seam_ok = mc.wide_ok && pl->t_raw[sc] && g.W * 3 >= 2 * kTSeamHalf && (long long)n_frames * g.H >= 2 && !lab_int("X360_NO_SEAM", 0);
+    memset(&mc.tms, 0, sizeof mc.tms);
+    if ((mc.stage_ok || mc.store_ok) &&
+        !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, mc.stage_ok != 0, out_views, n_frames * pl->p.n_views, g.oh, g.ow, t_th, mc.store_ok != 0,
+                           &mc.tms, pl->t_raw[sc], wide_rows, &mc.wide_ok, &mc.seam_ok)) {
+        mc.stage_ok = 0;                               // every tile goes direct, byte stores
+        mc.store_ok = 0;
+        mc.wide_ok = mc.seam_ok = false;
+    }
+    mc.frames = frames; mc.out = out_views; mc.n_frames = n_frames;
+    return &mc;
+}
+
+static int launch_score_pass(x360_plan *pl, const uint8_t *views, int n, int64_t *sum_lap, int64_t *sum_lap2, cudaStream_t st);
 
 static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint8_t *out_views, int64_t *sum_lap,
                         int64_t *sum_lap2, cudaStream_t st)
 {
     if (sum_lap && pl->split_score) {
-        // experiment (X360_SPLIT_SCORE=1): extraction without the fused score, then one streaming pass over the views
+        // extraction without the fused score, then one streaming pass over the finished views
         if (int rc = launch_tiled(pl, frames, n_frames, out_views, nullptr, nullptr, st)) return rc;
-        const Geom &g = pl->g;
-        const int n = n_frames * pl->p.n_views;
-        CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n, st));
-        CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n, st));
-        const int fast = ((uintptr_t)out_views % 4 == 0) && (g.ow % 4 == 0);
-        for (int n0 = 0; n0 < n; n0 += 32768) {
-            const int m = std::min(32768, n - n0);
-            blur_sums_views_kernel<<<dim3((unsigned)((g.ow + kBsW - 1) / kBsW), (unsigned)((g.oh + kBsH - 1) / kBsH), (unsigned)m), 256, 0, st>>>(
-                out_views + (size_t)n0 * g.oh * g.ow * 3, g.oh, g.ow, fast, (long long *)sum_lap + n0, (long long *)sum_lap2 + n0);
-            g_launches.fetch_add(1);
-        }
-        CU(cudaGetLastError());
-        return X360_OK;
+        return launch_score_pass(pl, out_views, n_frames * pl->p.n_views, sum_lap, sum_lap2, st);
     }
     const bool scores = sum_lap != nullptr;
     const Geom &g = pl->g;
@@ -460,8 +604,13 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.sum_lap2 = (long long *)sum_lap2;
     a.R = pl->d_R;
     a.lz_tab = pl->d_lz;
-    a.counter = pl->d_modes + 3;
-    a.tile_modes = pl->d_modes;
+    // this launch's slot of the scratch ring (work counter + tile-mode counters), zeroed on the launch stream
+    const int slot = pl->ring_next;
+    pl->ring_next = (slot + 1) % kRingSlots;
+    pl->ring_last = slot;
+    unsigned *scratch = pl->d_modes + (size_t)slot * kRingWords;
+    a.counter = scratch + 5;
+    a.tile_modes = scratch;
     a.F = n_frames;
     a.V = pl->p.n_views;
     const int sc = scores ? 1 : 0, t_rows = pl->t_rows[sc], t_th = pl->t_th[sc];
@@ -470,9 +619,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.tiles_y = (g.oh + t_th - 1) / t_th;
     a.col_u0 = pl->col_u0 ? 1 : 0;
     a.aligned = ((uintptr_t)frames % 4 == 0) && (g.W % 4 == 0);
-    a.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= t_rows && g.W * 3 >= 256;
-    a.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= t_th;
-    if (getenv("X360_NO_TMA_STORE") && atoi(getenv("X360_NO_TMA_STORE"))) a.store_ok = 0;
+    for (int c = 0; c < kTNumWide; ++c) a.wide_rows[c] = pl->wide_rows[sc][c];
 
     // Work items = units x tiles x frame chunks, enough of them for the dynamic scheduler to balance the
     // grid.  The map of a tile is evaluated once per item and the per-view setup once per (item, view), so
@@ -484,7 +631,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     int level = 0;
     while (level < 3 && pl->n_units[level] * tiles < want_items && pl->n_units[level + 1] > pl->n_units[level]) ++level;
     if (pl->n_units[level] * tiles < want_items && n_frames > 1) level = 0;   // chunking needed anyway: keep the sharing
-    if (const char *e = getenv("X360_UNIT_LEVEL")) level = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : level;
+    if (const char *e = lab_env("X360_UNIT_LEVEL")) level = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : level;
     const int n_units = pl->n_units[level];
     a.units = pl->d_units[level];
     a.unit_view = pl->d_unit_view[level];
@@ -494,7 +641,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     if (want_chunks < 1) want_chunks = 1;
     if (want_chunks > n_frames) want_chunks = n_frames;
     int FG = (int)((n_frames + want_chunks - 1) / want_chunks);
-    if (const char *e = getenv("X360_FG")) FG = atoi(e) > 0 ? atoi(e) : FG;
+    if (const char *e = lab_env("X360_FG")) FG = atoi(e) > 0 ? atoi(e) : FG;
     if (FG > n_frames) FG = n_frames;
     a.FG = FG;
     a.n_chunks = (n_frames + FG - 1) / FG;
@@ -502,22 +649,75 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     if (n_items > 0x7fffffff) return fail(X360_E_INVALID, "too many work items (%lld)", n_items);
     a.n_items = (int)n_items;
 
-    TiledMaps tms;
-    memset(&tms, 0, sizeof tms);
-    if ((a.stage_ok || a.store_ok) &&
-        !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, a.stage_ok != 0, out_views, n_frames * a.V, g.oh, g.ow, t_th, a.store_ok != 0, &tms,
-                           pl->t_raw[sc])) {
-        a.stage_ok = 0;                                   // every tile goes direct, byte stores
-        a.store_ok = 0;
-    }
-    CU(cudaMemsetAsync(pl->d_modes, 0, sizeof(unsigned) * 4, st));
+    const bool two = pl->two_launch[sc] && pl->d_defer[0] != nullptr;
+    const x360_plan::MapCache *mc = tiled_maps(pl, pl->maps[sc], frames, n_frames, out_views, sc, t_rows, pl->wide_rows[sc]);
+    const x360_plan::MapCache *mc2 = two ? tiled_maps(pl, pl->maps2[sc], frames, n_frames, out_views, sc, pl->t2_rows[sc], pl->wide_rows2[sc]) : nullptr;
+    a.stage_ok = mc->stage_ok;
+    a.store_ok = mc->store_ok;
+    a.wide_ok = mc->wide_ok ? 1 : 0;
+    a.seam_ok = mc->seam_ok ? 1 : 0;
+    CU(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * kRingWords, st));
     if (scores) {
         CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
     }
+    int db = -1;
+    if (two && mc->stage_ok && mc2->stage_ok) {
+        // the deferred-pair list of this launch pair: one of kDeferBufs buffers; a buffer still in use by an earlier launch
+        // pair (another stream) is waited for on this stream
+        db = pl->defer_next;
+        pl->defer_next = (db + 1) % x360_plan::kDeferBufs;
+        if (pl->defer_used[db]) CU(cudaStreamWaitEvent(st, pl->defer_ev[db], 0));
+        a.mode = 1;
+        a.defer_cap = pl->defer_cap;
+        a.defer_sub = lab_int("X360_DEFER_SUB", n_frames >= 16 ? 4 : (n_frames >= 4 ? 2 : 1));
+        a.defer_list = pl->d_defer[db];
+        a.defer_count = pl->d_defer[db] + 2 * (size_t)pl->defer_cap;
+        CU(cudaMemsetAsync(a.defer_count, 0, sizeof(unsigned), st));
+    }
     const int grid = (int)std::min<long long>(n_items, cap);
-    pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0, pl->t_raw[sc])<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, tms);
+    const tiled_fn fn = pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0, pl->t_raw[sc]);
+    fn<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, mc->tms);
     g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    if (db >= 0) {
+        a.mode = 2;
+        a.counter = scratch + 6;
+        a.rows_max = pl->t2_rows[sc];
+        a.bw_max = pl->t2_bw[sc];
+        for (int c = 0; c < kTNumWide; ++c) a.wide_rows[c] = pl->wide_rows2[sc][c];
+        a.stage_ok = mc2->stage_ok;
+        a.store_ok = mc2->store_ok;
+        a.wide_ok = mc2->wide_ok ? 1 : 0;
+        a.seam_ok = mc2->seam_ok ? 1 : 0;
+        fn<<<pl->grid_cap2[sc], 32 * tiled_warps(scores, t_th), pl->t2_smem[sc], st>>>(a, mc2->tms);
+        g_launches.fetch_add(1);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(pl->defer_ev[db], st));
+        pl->defer_used[db] = true;
+    }
+    return X360_OK;
+}
+
+// The split score: one streaming pass over finished views (blur_sums_views_kernel, x360_misc.cuh)
+static int launch_score_pass(x360_plan *pl, const uint8_t *views, int n, int64_t *sum_lap, int64_t *sum_lap2, cudaStream_t st)
+{
+    const Geom &g = pl->g;
+    CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n, st));
+    CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n, st));
+    const int fast = ((uintptr_t)views % 4 == 0) && (g.ow % 4 == 0);
+    const bool march = fast && g.ow >= 8 && g.oh >= 2 && !lab_int("X360_SCORE_TILES", 0);
+    for (int n0 = 0; n0 < n; n0 += 32768) {
+        const int m = std::min(32768, n - n0);
+        const uint8_t *v0 = views + (size_t)n0 * g.oh * g.ow * 3;
+        if (march)
+            blur_sums_march_kernel<<<dim3((unsigned)((g.ow + kScStride - 1) / kScStride), (unsigned)((g.oh + kScWarps * kScRows - 1) / (kScWarps * kScRows)), (unsigned)m),
+                                     32 * kScWarps, 0, st>>>(v0, g.oh, g.ow, (long long *)sum_lap + n0, (long long *)sum_lap2 + n0);
+        else
+            blur_sums_views_kernel<<<dim3((unsigned)((g.ow + kBsW - 1) / kBsW), (unsigned)((g.oh + kBsH - 1) / kBsH), (unsigned)m), 256, 0, st>>>(
+                v0, g.oh, g.ow, fast, (long long *)sum_lap + n0, (long long *)sum_lap2 + n0);
+        g_launches.fetch_add(1);
+    }
     CU(cudaGetLastError());
     return X360_OK;
 }
@@ -557,7 +757,7 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
     for (int sc = 0; sc < 2; ++sc) {
         int rows = 0, bw = 0, th = 0;
         choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
-                        params->n_views, params->interp == X360_INTERP_LANCZOS4, sc != 0, raw_allowed(), &rows, &bw, &th);
+                        params->n_views, params->interp == X360_INTERP_LANCZOS4, sc != 0, plan_opts(params->flags), &rows, &bw, &th);
         if (rows_max) rows_max[sc] = rows;
         if (bw_max) bw_max[sc] = bw;
         if (tile_h) tile_h[sc] = th;
@@ -577,8 +777,13 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (params->interp != X360_INTERP_LINEAR && params->interp != X360_INTERP_LANCZOS4)
         return fail(X360_E_INVALID, "unknown interp %d", params->interp);
     if (params->path < X360_PATH_AUTO || params->path > X360_PATH_TILED) return fail(X360_E_INVALID, "unknown path %d", params->path);
+#ifdef X360_LAB
     if (params->path == X360_PATH_STAGED && params->interp == X360_INTERP_LANCZOS4)
         return fail(X360_E_UNSUPPORTED, "the staged path is built for bilinear only; Lanczos4 uses the tiled or the direct path");
+#else
+    if (params->path == X360_PATH_DIRECT || params->path == X360_PATH_STAGED)
+        return fail(X360_E_UNSUPPORTED, "path %d is a comparison kernel, compiled only into -DX360_LAB builds of libx360", params->path);
+#endif
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
         return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
@@ -601,38 +806,54 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     if (pl->path == X360_PATH_TILED) {
         // staging capacity and tile height from a host survey of the tiles' footprints, without / with the score halo
         const bool lz = params->interp == X360_INTERP_LANCZOS4;
-        pl->col_u0 = column_only_map_x(params->R, params->n_views) && !(getenv("X360_NO_COL_U0") && atoi(getenv("X360_NO_COL_U0")));
-        const bool allow_raw = raw_allowed();
-        if (const char *e = getenv("X360_SPLIT_SCORE")) pl->split_score = atoi(e) != 0;
+        pl->opts = plan_opts(params->flags);
+        pl->col_u0 = column_only_map_x(params->R, params->n_views) && !lab_int("X360_NO_COL_U0", 0);
+        pl->split_score = score_is_split(pl->opts);
+        long long unfit[2] = {0, 0};
         for (int sc = 0; sc < 2; ++sc) {
             int rows = 40, bw = 144, th = 32;
-            choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, allow_raw, &rows, &bw, &th);
-            const bool raw = tiled_raw(sc != 0, lz, th, pl->col_u0, allow_raw);
+            choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, pl->opts, &rows, &bw, &th, &unfit[sc]);
+            const bool raw = tiled_raw(sc != 0, lz, pl->opts);
             pl->t_raw[sc] = raw;
-            if (const char *e = getenv("X360_TILED_BW")) {
+            if (const char *e = lab_env("X360_TILED_BW")) {
                 const int v = atoi(e), unit = raw ? 64 : 48;
                 bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
             }
-            if (const char *e = getenv("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw) > 110 * 1024) rows -= kTBoxRows;
+            if (const char *e = lab_env("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
+            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw) > (size_t)kTiledSmemCap) rows -= kTBoxRows;
             pl->t_th[sc] = th;
             pl->t_bw[sc] = bw;
             pl->t_rows[sc] = rows;
+            wide_class_rows(rows, bw, pl->wide_rows[sc]);
             pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw);
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0, raw), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->t_smem[sc]);
+            // the limit belongs to the kernel function, not to this plan: always the common cap (see kTiledSmemCap)
+            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0, raw), cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemCap);
             if (ea != cudaSuccess) {
-                const size_t want = pl->t_smem[sc];
                 delete pl;
-                return fail(X360_E_CUDA, "cannot reserve %zu B of shared memory: %s", want, cudaGetErrorString(ea));
+                return fail(X360_E_CUDA, "cannot reserve %d B of shared memory: %s", kTiledSmemCap, cudaGetErrorString(ea));
+            }
+            pl->grid_cap[sc] = pl->sm_count * tiled_occupancy(pl, sc, pl->t_smem[sc]);
+            // a second launch with 16 KB staging buffers where the survey found footprints beyond this capacity (pole faces)
+            const int rows2 = lab_int("X360_T2_ROWS", 64), bw2 = lab_int("X360_T2_BW", raw ? 256 : 240);
+            if (!lz && !(raw && pl->col_u0) && !pl->opts.no_wide && unfit[sc] > 0 && rows2 * bw2 > rows * bw && !lab_int("X360_ONE_LAUNCH", 0)) {
+                pl->t2_rows[sc] = rows2;
+                pl->t2_bw[sc] = bw2;
+                wide_class_rows(rows2, bw2, pl->wide_rows2[sc]);
+                pl->t2_smem[sc] = tiled_smem_bytes(rows2, bw2, sc != 0, lz, th, pl->col_u0, raw);
+                if (pl->t2_smem[sc] <= (size_t)kTiledSmemCap) {
+                    pl->grid_cap2[sc] = pl->sm_count * tiled_occupancy(pl, sc, pl->t2_smem[sc]);
+                    pl->two_launch[sc] = true;
+                }
             }
         }
     }
+#ifdef X360_LAB
     if (pl->path == X360_PATH_STAGED) {
         // Footprint capacity: a 34-px tile side (32 + halo) times the source/output scale at the view
         // centre, with head-room for shear and latitude stretch; anything larger goes direct.
         const double scale = ((double)params->src_w / (2.0 * 3.14159265358979323846)) / pl->g.f;
         double factor = 1.4;
-        if (const char *e = getenv("X360_STAGE_FACTOR")) factor = atof(e) > 0.5 ? atof(e) : factor;
+        if (const char *e = lab_env("X360_STAGE_FACTOR")) factor = atof(e) > 0.5 ? atof(e) : factor;
         int cap = round_up((int)std::ceil((kTile + 2) * scale * factor) + 8, 4);
         cap = cap < 16 ? 16 : (cap > 128 ? 128 : cap);
         for (;; cap -= 4) {                                   // shrink until two CTAs fit one SM
@@ -641,18 +862,27 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
             if (pl->smem <= 110 * 1024 || cap <= 16) break;
         }
         for (int sc = 0; sc < 2; ++sc) {
-            const cudaError_t ea = cudaFuncSetAttribute(pick_staged(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+            const cudaError_t ea = cudaFuncSetAttribute(pick_staged(sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
             if (ea != cudaSuccess) {
                 delete pl;
                 return fail(X360_E_CUDA, "cannot reserve %zu B of shared memory: %s", pl->smem, cudaGetErrorString(ea));
             }
         }
     }
+#endif
     cudaError_t e = cudaMalloc(&pl->d_R, sizeof(double) * 9 * params->n_views);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_modes, sizeof(unsigned) * 4);
-    if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_modes, sizeof(unsigned) * kRingSlots * kRingWords);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * kRingSlots * kRingWords);
+    if (e == cudaSuccess && (pl->two_launch[0] || pl->two_launch[1])) {
+        const long long pairs = (long long)params->n_views * pl->g.tiles_x * ((pl->g.oh + 15) / 16) * 8;      // (tile, view, frame chunk) triples, generously
+        pl->defer_cap = (int)std::min<long long>(pairs, 1 << 18);
+        for (int i = 0; i < x360_plan::kDeferBufs && e == cudaSuccess; ++i) {
+            e = cudaMalloc(&pl->d_defer[i], sizeof(unsigned) * (2 * (size_t)pl->defer_cap + 1));
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->defer_ev[i], cudaEventDisableTiming);
+        }
+    }
     if (e == cudaSuccess && pl->path == X360_PATH_TILED) {
-        const bool share = !(getenv("X360_NO_SHARE") && atoi(getenv("X360_NO_SHARE")));
+        const bool share = !lab_int("X360_NO_SHARE", 0);
         for (int lv = 0; lv < 4 && e == cudaSuccess; ++lv) {
             const HostUnits h = build_units(params->R, params->n_views, params->src_w, pl->g, share, kTMaxUnitViews >> lv);
             pl->n_units[lv] = (int)h.units.size();
@@ -685,6 +915,10 @@ int x360_plan_destroy(x360_plan *pl)
     cudaFree(pl->d_R);
     cudaFree(pl->d_lz);
     cudaFree(pl->d_modes);
+    for (int i = 0; i < x360_plan::kDeferBufs; ++i) {
+        cudaFree(pl->d_defer[i]);
+        if (pl->defer_ev[i]) cudaEventDestroy(pl->defer_ev[i]);
+    }
     for (int lv = 0; lv < 4; ++lv) {
         cudaFree(pl->d_units[lv]);
         cudaFree(pl->d_unit_view[lv]);
@@ -732,12 +966,12 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     return X360_OK;
 }
 
-int x360_plan_tile_modes(x360_plan *pl, uint32_t *out3)
+int x360_plan_tile_modes(x360_plan *pl, uint32_t *out5)
 {
-    if (!pl || !out3) return fail(X360_E_INVALID, "null argument");
+    if (!pl || !out5) return fail(X360_E_INVALID, "null argument");
     CU(cudaSetDevice(pl->p.device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out3, pl->d_modes, sizeof(unsigned) * 3, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out5, pl->d_modes + (size_t)pl->ring_last * kRingWords, sizeof(unsigned) * 5, cudaMemcpyDeviceToHost));
     return X360_OK;
 }
 
@@ -752,6 +986,7 @@ int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const bool scores = sum_lap != nullptr;
     if (pl->path == X360_PATH_TILED) return launch_tiled(pl, frames, n_frames, out_views, sum_lap, sum_lap2, st);
+#ifdef X360_LAB
     ExtractArgs a;
     a.g = pl->g;
     a.frames = frames;
@@ -769,7 +1004,8 @@ int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, 
                  pl->g.W * 3 >= kMaxBoxBytes;
     a.rows_max = pl->rows_max; a.px_max = pl->px_max; a.pp = pl->pp; a.raw_pitch = pl->raw_pitch;
     a.tile_modes = pl->d_modes;
-    CU(cudaMemsetAsync(pl->d_modes, 0, sizeof(unsigned) * 3, st));
+    pl->ring_last = 0;
+    CU(cudaMemsetAsync(pl->d_modes, 0, sizeof(unsigned) * kRingWords, st));
     if (scores) {
         CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
         CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
@@ -786,31 +1022,66 @@ int x360_extract_device(x360_plan *pl, const uint8_t *frames, int32_t n_frames, 
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return X360_OK;
+#else
+    (void)scores;
+    return fail(X360_E_UNSUPPORTED, "plan path %d is not compiled into this build", pl->path);
+#endif
 }
 
 static int unsharp_launch(const uint8_t *d_in, long long n, int h, int w, double strength, uint8_t *d_out, cudaStream_t st);
 
+// Streams, events and the two chunk buffers of the pipelined host path.  Idempotent: a call that failed half-way leaves
+// what it created in the plan, the next call creates only what is still missing (x360_plan_destroy frees everything).
 static int pipe_setup(x360_plan *pl)
 {
-    if (pl->pipe_ready && pl->sharpen && !pl->d_sharp[0]) {
-        const size_t vb = (size_t)pl->g.oh * pl->g.ow * 3 * pl->p.n_views;
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&pl->d_sharp[i], vb * pl->chunk));
-    }
-    if (pl->pipe_ready) return X360_OK;
+    if (pl->pipe_ready && !(pl->sharpen && !pl->d_sharp[1])) return X360_OK;
     const size_t fb = (size_t)pl->g.H * pl->g.W * 3, vb = (size_t)pl->g.oh * pl->g.ow * 3 * pl->p.n_views;
-    CU(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&pl->s_k, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+    if (!pl->s_in) CU(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+    if (!pl->s_k) CU(cudaStreamCreateWithFlags(&pl->s_k, cudaStreamNonBlocking));
+    if (!pl->s_out) CU(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        CU(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&pl->ev_k[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
-        CU(cudaMalloc(&pl->d_frames[i], fb * pl->chunk));
-        CU(cudaMalloc(&pl->d_views[i], vb * pl->chunk));
-        if (pl->sharpen) CU(cudaMalloc(&pl->d_sharp[i], vb * pl->chunk));
-        CU(cudaMalloc(&pl->d_sums[i], sizeof(long long) * 2 * pl->chunk * pl->p.n_views));
+        if (!pl->ev_in[i]) CU(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+        if (!pl->ev_k[i]) CU(cudaEventCreateWithFlags(&pl->ev_k[i], cudaEventDisableTiming));
+        if (!pl->ev_out[i]) CU(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
+        if (!pl->d_frames[i]) CU(cudaMalloc(&pl->d_frames[i], fb * pl->chunk));
+        if (!pl->d_views[i]) CU(cudaMalloc(&pl->d_views[i], vb * pl->chunk));
+        if (pl->sharpen && !pl->d_sharp[i]) CU(cudaMalloc(&pl->d_sharp[i], vb * pl->chunk));
+        if (!pl->d_sums[i]) CU(cudaMalloc(&pl->d_sums[i], sizeof(long long) * 2 * pl->chunk * pl->p.n_views));
     }
     pl->pipe_ready = true;
+    return X360_OK;
+}
+
+// one chunk of the pipeline (see x360_extract_host); any failure is reported to the caller, which drains the streams
+static int pipe_chunk(x360_plan *pl, int c, const uint8_t *frames, int f0, int n, uint8_t *out_views, int64_t *sum_lap, int64_t *sum_lap2)
+{
+    const int b = c & 1, V = pl->p.n_views;
+    const size_t fb = (size_t)pl->g.H * pl->g.W * 3, vb = (size_t)pl->g.oh * pl->g.ow * 3 * V;
+    const bool scores = sum_lap != nullptr;
+    // upload: the input buffer is free once the kernel of chunk c-2 has run
+    if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
+    CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+    CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
+    // compute: needs the upload, and the download of chunk c-2 out of this output buffer
+    CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
+    if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));
+    long long *ds = scores ? pl->d_sums[b] : nullptr;
+    long long *ds2 = scores ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
+    if (int rc = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return rc;
+    const uint8_t *d_result = pl->d_views[b];
+    if (pl->sharpen) {                          // processor.py:379-381 on the chunk's views, still on the device
+        if (int rc = unsharp_launch(pl->d_views[b], (long long)n * V, pl->g.oh, pl->g.ow, pl->sharpen_strength, pl->d_sharp[b], pl->s_k)) return rc;
+        d_result = pl->d_sharp[b];
+    }
+    CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
+    // download
+    CU(cudaStreamWaitEvent(pl->s_out, pl->ev_k[b], 0));
+    CU(cudaMemcpyAsync(out_views + (size_t)f0 * vb, d_result, vb * n, cudaMemcpyDeviceToHost, pl->s_out));
+    if (scores) {
+        CU(cudaMemcpyAsync(sum_lap + (size_t)f0 * V, ds, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
+        CU(cudaMemcpyAsync(sum_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
+    }
+    CU(cudaEventRecord(pl->ev_out[b], pl->s_out));
     return X360_OK;
 }
 
@@ -823,41 +1094,16 @@ int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, ui
     if (n_frames == 0) return X360_OK;
     CU(cudaSetDevice(pl->p.device));
     if (int rc = pipe_setup(pl)) return rc;
-    const int V = pl->p.n_views;
-    const size_t fb = (size_t)pl->g.H * pl->g.W * 3, vb = (size_t)pl->g.oh * pl->g.ow * 3 * V;
-    const bool scores = sum_lap != nullptr;
-    int c = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += pl->chunk, ++c) {
-        const int b = c & 1;
-        const int n = (n_frames - f0 < pl->chunk) ? n_frames - f0 : pl->chunk;
-        // upload: the input buffer is free once the kernel of chunk c-2 has run
-        if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
-        CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
-        CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
-        // compute: needs the upload, and the download of chunk c-2 out of this output buffer
-        CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
-        if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));
-        long long *ds = scores ? pl->d_sums[b] : nullptr;
-        long long *ds2 = scores ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
-        if (int rc = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return rc;
-        const uint8_t *d_result = pl->d_views[b];
-        if (pl->sharpen) {                          // processor.py:379-381 on the chunk's views, still on the device
-            if (int rc = unsharp_launch(pl->d_views[b], (long long)n * V, pl->g.oh, pl->g.ow, pl->sharpen_strength, pl->d_sharp[b], pl->s_k)) return rc;
-            d_result = pl->d_sharp[b];
-        }
-        CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
-        // download
-        CU(cudaStreamWaitEvent(pl->s_out, pl->ev_k[b], 0));
-        CU(cudaMemcpyAsync(out_views + (size_t)f0 * vb, d_result, vb * n, cudaMemcpyDeviceToHost, pl->s_out));
-        if (scores) {
-            CU(cudaMemcpyAsync(sum_lap + (size_t)f0 * V, ds, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
-            CU(cudaMemcpyAsync(sum_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * n * V, cudaMemcpyDeviceToHost, pl->s_out));
-        }
-        CU(cudaEventRecord(pl->ev_out[b], pl->s_out));
-    }
-    CU(cudaStreamSynchronize(pl->s_out));
-    CU(cudaStreamSynchronize(pl->s_k));
-    CU(cudaStreamSynchronize(pl->s_in));
+    int rc = X360_OK, c = 0;
+    for (int f0 = 0; f0 < n_frames && rc == X360_OK; f0 += pl->chunk, ++c)
+        rc = pipe_chunk(pl, c, frames, f0, (n_frames - f0 < pl->chunk) ? n_frames - f0 : pl->chunk, out_views, sum_lap, sum_lap2);
+    // Drain all three streams on EVERY exit: copies still in flight target the caller's buffers, which it may free as
+    // soon as this function has returned (with an error as much as with success).
+    const std::string first_error = rc != X360_OK ? g_err : std::string();
+    const cudaError_t e_out = cudaStreamSynchronize(pl->s_out), e_k = cudaStreamSynchronize(pl->s_k), e_in = cudaStreamSynchronize(pl->s_in);
+    if (rc != X360_OK) { g_err = first_error; return rc; }
+    for (cudaError_t e : {e_out, e_k, e_in})
+        if (e != cudaSuccess) return fail(X360_E_CUDA, "pipelined extraction failed: %s", cudaGetErrorString(e));
     return X360_OK;
 }
 
@@ -980,7 +1226,7 @@ static int unsharp_launch(const uint8_t *d_in, long long n, int h, int w, double
     const float alpha = (float)(1.0 + strength), beta = (float)(-strength);       // addWeighted casts its scalars to float
     const size_t pitch = (size_t)w * 3;
     bool tiled = (pitch % 16 == 0) && pitch >= (size_t)kUsBoxW && h >= kUsRows && ((uintptr_t)d_in % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
-    if (const char *e = getenv("X360_UNSHARP_GENERIC")) tiled = tiled && !atoi(e);
+    if (lab_int("X360_UNSHARP_GENERIC", 0)) tiled = false;
     UnsharpMaps tms;
     memset(&tms, 0, sizeof tms);
     if (tiled) {

@@ -176,6 +176,82 @@ blur_sums_views_kernel(const uint8_t *__restrict__ views, int h, int w, int fast
     }
 }
 
+// The same sums by MARCHING down the view (the split score pass of plans that run it, launch_score_pass): a warp owns a
+// 128-pixel-wide column strip (lane = 4 pixels = 12 packed bytes = 3 coalesced LDG.32) and walks kScRows rows down it with
+// the gray words of rows y-1, y, y+1 in registers, so every pixel is loaded and converted once and nothing goes through
+// shared memory: left / right neighbours are the adjacent lanes' words (2 SHFL per 4 pixels).  Strips overlap by one lane on
+// either side (stride 120 pixels): lanes 0 and 31 only provide their neighbours' halo.  image_utils.py:22-27, reflect-101.
+// Needs w % 4 == 0, a 4-byte aligned base, w >= 8 and h >= 2 (anything else takes blur_sums_views_kernel).
+constexpr int kScRows = 32, kScStride = 120, kScWarps = 8;
+
+__device__ __forceinline__ uint32_t gray4_of(uint32_t w0, uint32_t w1, uint32_t w2)      // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+{
+    const uint32_t g0 = gray_of(w0), g1 = gray_of(__byte_perm(w0, w1, 0x0543));
+    const uint32_t g2 = gray_of(__byte_perm(w1, w2, 0x0432)), g3 = gray_of(w2 >> 8);
+    return __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
+}
+
+__global__ void __launch_bounds__(32 * kScWarps)
+blur_sums_march_kernel(const uint8_t *__restrict__ views, int h, int w, long long *__restrict__ sum, long long *__restrict__ sum2)
+{
+    __shared__ int red[kScWarps][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x = (int)blockIdx.x * kScStride - 4 + 4 * lane;                 // this lane's four pixels x .. x+3
+    const int r0 = ((int)blockIdx.y * kScWarps + warp) * kScRows, r1 = min(r0 + kScRows, h);
+    const bool live = x >= 0 && x < w;
+    const uint32_t *img = reinterpret_cast<const uint32_t *>(views + (size_t)blockIdx.z * h * w * 3);
+    const size_t pitch_w = (size_t)w * 3 / 4;                                 // words per row
+    const size_t col_w = live ? (size_t)x * 3 / 4 : 0;
+    int pl = 0;
+    unsigned pl2 = 0;
+    if (r0 < h) {
+        auto load_row = [&](int y, uint32_t (&r)[3]) {
+            const uint32_t *src = img + (size_t)y * pitch_w + col_w;
+            r[0] = live ? __ldg(src) : 0u; r[1] = live ? __ldg(src + 1) : 0u; r[2] = live ? __ldg(src + 2) : 0u;
+        };
+        uint32_t ra[3], rb[3], rc[3];
+        load_row(r0 == 0 ? 1 : r0 - 1, ra);
+        load_row(r0, rb);
+        load_row(min(r0 + 1, h - 1), rc);
+        uint32_t U = gray4_of(ra[0], ra[1], ra[2]), C = gray4_of(rb[0], rb[1], rb[2]);
+        const bool counts = live && lane > 0 && lane < 31;                    // lanes 0 / 31: halo providers
+        const bool at_left = x == 0, at_right = x + 3 == w - 1;
+#pragma unroll 2
+        for (int y = r0; y < r1; ++y) {
+            uint32_t D = (y + 1 < h) ? gray4_of(rc[0], rc[1], rc[2]) : U;     // reflect-101: g[h] = g[h-2]
+            if (y + 2 < r1 + 1 && y + 2 < h) load_row(y + 2, rc);             // two rows ahead of the one being summed
+            uint32_t l = __shfl_up_sync(0xffffffffu, C, 1) >> 24, r = __shfl_down_sync(0xffffffffu, C, 1) & 0xffu;
+            if (at_left) l = (C >> 8) & 0xffu;                                // g[-1] = g[1]
+            if (at_right) r = (C >> 16) & 0xffu;                              // g[w] = g[w-2]
+            const uint32_t Lw = __byte_perm(C, l, 0x2104);                    // [l, c0, c1, c2]
+            const uint32_t Rw = __byte_perm(C, r, 0x4321);                    // [c1, c2, c3, r]
+            constexpr uint32_t kA = 0x0001fc01u;                              // [ 1, -4,  1,  0]
+            constexpr uint32_t kB = 0x01fc0100u;                              // [ 0,  1, -4,  1]
+            const int L0 = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
+            const int L1 = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
+            const int L2 = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
+            const int L3 = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
+            if (counts) {
+                pl += L0 + L1 + L2 + L3;
+                pl2 += (unsigned)(L0 * L0) + (unsigned)(L1 * L1) + (unsigned)(L2 * L2) + (unsigned)(L3 * L3);
+            }
+            U = C;
+            C = D;
+        }
+    }
+    pl = __reduce_add_sync(0xffffffffu, pl);
+    pl2 = __reduce_add_sync(0xffffffffu, pl2);                                // <= 30 lanes x 32 rows x 4 x 1020^2 < 2^32
+    if (lane == 0) { red[warp][0] = pl; red[warp][1] = (int)pl2; }
+    __syncthreads();
+    if (tid == 0) {
+        long long s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < kScWarps; ++k) { s1 += red[k][0]; s2 += (unsigned)red[k][1]; }
+        atomicAdd((unsigned long long *)&sum[blockIdx.z], (unsigned long long)s1);
+        atomicAdd((unsigned long long *)&sum2[blockIdx.z], (unsigned long long)s2);
+    }
+}
+
 // hand the views of the selected faces to the masker without leaving the device.
 // src/core/processor.py:392-420 passes the BGR views (all of them, or the faces named in 'ai_mask_cameras') to
 // AIService.process_batch (src/core/ai_model.py:125-167), whose model turns each image into a normalised

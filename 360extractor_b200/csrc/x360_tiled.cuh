@@ -66,9 +66,27 @@ constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
 #endif
 constexpr int kTRawBufs = X360_RAW_NB;   // raw buffers of the raw-gather variant (the TMA box of frame f + NB - 1 flies during frame f)
 
+// Wide boxes: tiles whose footprint is wider than the regular capacity but still fits the raw buffer as a flatter box
+// (near the poles a 32-px tile spans 32 / r rad of longitude at r px from the pole; the footprint is a few rows of
+// many pixels).  Width classes in bytes (multiples of 192 = lcm(48, 64): valid row pitches for both gathers), loaded
+// through a uint32 view of the frame (a TMA box has at most 256 elements per dimension); the class height is whatever
+// the raw buffer holds, TiledArgs::wide_rows.
+constexpr int kTNumWide = 4;
+__host__ __device__ constexpr int tiled_wide_bw(int c) { return 384 + 192 * c; }     // 384, 576, 768, 960
+// Seam boxes (raw gather): a tile whose footprint wraps the +-pi seam reads columns [xa, W) and [0, xb] of each source
+// row.  Frames are dense, so the bytes after column W-1 of row y are columns 0.. of row y+1: one box over a "window
+// tensor" — base = frames + 3W - kTSeamHalf, rows of 2 kTSeamHalf bytes, row pitch 3W — brings row y's tail and row
+// y+1's head side by side.  Regular widths 64 k (k <= 4) at the full box height, then the wide classes.
+constexpr int kTSeamHalf = 1024;
+constexpr int kTNumSeam = 4 + kTNumWide;
+constexpr int kTMapWide0 = kTNumBox, kTMapSeam0 = kTMapWide0 + kTNumWide, kTMapOut = kTMapSeam0 + kTNumSeam, kTNumMaps = kTMapOut + 1;
+
 struct TiledMaps {
-    CUtensorMap in[kTNumBox];         // uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]; raw gather: {64 (w + 1), ..}, w < 4
-    CUtensorMap out;                  // uint8 [F*V][oh][3 ow], box {96, tile height, 1}
+    // [0, 15)  uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]; raw gather: {64 (w + 1), ..}, w < 4
+    // [15, 19) wide: uint32 [F][H][3W/4], box {tiled_wide_bw(c) / 4, wide_rows[c], 1}
+    // [19, 27) seam: window tensor [1][F H - 1][2 kTSeamHalf] (uint8: widths 64 (w + 1) x rows_max; uint32: the wide classes)
+    // [27]     out: uint8 [F*V][oh][3 ow], box {96, tile height, 1}
+    CUtensorMap m[kTNumMaps];
 };
 
 // One view unit: `n` views starting at `first` in the (view id, shift) tables share a map.
@@ -96,6 +114,14 @@ struct TiledArgs {
     int rows_max, bw_max;             // staging capacity: footprint rows, raw bytes per footprint row (48 k)
     int tiles_y;                      // tile rows per view (tile height 32 or 16)
     int col_u0;                       // map_x of every view is independent of the output row (R01 = R21 = 0: yaw-only rotations)
+    int wide_ok, seam_ok;             // wide / seam tensor maps are encoded
+    // Two-launch mode: the first launch (mode 1) runs at the capacity that keeps the most CTAs per SM and, instead of gathering
+    // a (tile, view) whose footprint does not fit from global memory, appends {item, view-in-unit} to defer_list; the second
+    // launch (mode 2: larger buffers, fewer CTAs per SM) takes its items from that list, each cut into defer_sub frame ranges.
+    // mode 0: one launch, such tiles go straight to the direct gathers.
+    int mode, defer_cap, defer_sub;
+    unsigned *defer_list, *defer_count;
+    int wide_rows[kTNumWide];         // box height of each wide class (raw buffer bytes / class width, at most 256)
 };
 
 struct TiledCtrl {
@@ -103,6 +129,12 @@ struct TiledCtrl {
     unsigned long long mbar[3];       // one per raw buffer
     int wsum[kTWMax][2];                 // per-warp (sum L, sum L^2) of the current frame's tile (exact in 32 bits)
     int item;
+    int pad0;
+    // the TMA box of the current (tile, view), written and read by thread 0 only: coordinates of frame f are
+    // {cx, cy0 + f cyf, f czf}; `bytes` = box bytes, `map` = index into TiledMaps::m
+    int box_cx, box_cy0, box_cyf, box_czf, box_bytes, box_map;
+    int seam_ea, seam_rows;           // seam boxes: byte column of a row's end inside the box row; box rows in use
+    int def_vi, def_sub, def_took;    // second launch: view-in-unit and frame sub-range of the item; first launch: the pair was deferred
 };
 
 // Dynamic shared memory, fixed offsets first so every hot address is base + constant:
@@ -118,8 +150,8 @@ struct TiledCtrl {
 //        (scripts/bank_sim.py planes).  Row r, pixel x: lo at r * 4 bw/3 + 4 x, hi at r * 2 bw/3 + 2 x.
 //        Lanczos4 keeps contiguous 8-byte records (4 LDS.64 per source row), row pitch 8 bw/3.
 constexpr uint32_t kOffCtl = 0;
-constexpr uint32_t kOffTile = 128;
-static_assert(sizeof(TiledCtrl) <= 128, "ctrl block");
+constexpr uint32_t kOffTile = 256;
+static_assert(sizeof(TiledCtrl) <= 256, "ctrl block");
 
 // gray tile (TH rows + 1-px halo): rows -1..TH as compact 32-B rows, left / right halo columns apart
 template <int TH> struct TGray {
@@ -510,17 +542,43 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
 
     for (;;) {
         __syncthreads();                                   // previous item's shared state is dead
-        if (tid == 0) ctl.item = (int)atomicAdd(a.counter, 1u);
+        // DEFER: the two-launch mode exists in every variant but the raw gather of column-only plans (yaw-only views never
+        // come near a pole; their 64-register build has no room for it)
+        constexpr bool DEFER = !(RAW && COLSEL);
+        if (tid == 0) {
+            int it0 = (int)atomicAdd(a.counter, 1u);
+            if (DEFER && a.mode == 2) {                        // items of the second launch: the pairs the first one deferred
+                const unsigned n_def = min(*a.defer_count, (unsigned)a.defer_cap);
+                if ((unsigned)it0 >= n_def * (unsigned)a.defer_sub) it0 = INT_MAX;
+                else {
+                    const int e = it0 / a.defer_sub;
+                    ctl.def_sub = it0 - e * a.defer_sub;
+                    ctl.def_vi = (int)a.defer_list[2 * e + 1];
+                    it0 = (int)a.defer_list[2 * e];
+                }
+            }
+            ctl.item = it0;
+        }
         __syncthreads();
+        // (everything below comes from shared memory at CTA-uniform addresses: the compiler keeps item, tile, frame range and
+        // what derives from them — buffer indices, row pitches — in uniform registers)
         const int item = ctl.item;
         if (item >= a.n_items) break;
+        const int only_vi = (DEFER && a.mode == 2) ? ctl.def_vi : -1, sub = (DEFER && a.mode == 2) ? ctl.def_sub : 0;
         const int per_unit = tiles_per_view * a.n_chunks;      // every unit has the same number of items
         const int u = item / per_unit, local = item - u * per_unit;
-        const TiledUnit unit = a.units[u];
+        TiledUnit unit = a.units[u];
+        if (only_vi >= 0) { unit.first += only_vi; unit.n = 1; }   // second launch: the one deferred view, as a unit of its own
         const int chunk = local / tiles_per_view, tile = local - chunk * tiles_per_view;
         const int ty = tile / g.tiles_x;
         const int x0 = (tile - ty * g.tiles_x) * kTile, y0 = ty * TH;
-        const int f_begin = chunk * a.FG, f_end = min(a.F, f_begin + a.FG);
+        int f_begin = chunk * a.FG, f_end = min(a.F, f_begin + a.FG);
+        if (DEFER && a.mode == 2) {                            // this item's share of the chunk's frames
+            const int len = (f_end - f_begin + a.defer_sub - 1) / a.defer_sub;
+            f_begin += sub * len;
+            f_end = min(f_end, f_begin + len);
+            if (f_begin >= f_end) continue;
+        }
         const bool full = (x0 + kTile <= g.ow) && (y0 + TH <= g.oh);
 
         // ---- 1. the unit's map for this tile, to shared memory: fp64 map_x, Q5 map_y -------------
@@ -557,7 +615,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
 
         for (int vi = 0; vi < unit.n; ++vi) {
             const int v = a.unit_view[unit.first + vi];
-            const double shift = a.unit_shift[unit.first + vi];
+            const double shift = (DEFER && a.mode == 2) ? 0.0 : a.unit_shift[unit.first + vi];   // second launch: the view's own map (unit of one)
 
             // ---- 2. this view's Q5 coordinates and the footprint bounding box ----------------
             constexpr int NS = SCORES ? kTP + 1 : kTP;
@@ -598,20 +656,75 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             // footprint of the taps: bilinear (ix, iy) .. (+1, +1); Lanczos4 (ix-3, iy-3) .. (ix+4, iy+4).
             // Pair records for x in [x_org, xmax + MX1 - 1], source rows [y_org, ymax + MY1].
             constexpr int MX0 = LZ ? 3 : 0, MX1 = LZ ? 4 : 1, MY0 = LZ ? 3 : 0, MY1 = LZ ? 4 : 1;
-            const int x_org = RAW ? xmin : ((xmin - MX0) & ~3), y_org = ymin - MY0;
+            // RAW: a footprint across the +-pi seam (columns near W-1 and near 0, or a tap at column W) is re-measured in
+            // unwrapped columns — those left of W/2 continue past W — and staged through the seam window (kTSeamHalf)
+            bool seam = false;
+            if (RAW && a.seam_ok && (xmax - xmin > (g.W >> 1) || xmax + MX1 > g.W - 1)) {      // uniform over the CTA
+                int lo = INT_MAX, hi = INT_MIN;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    int ix = sxs[k] >> 5;
+                    ix += (ix < (g.W >> 1)) ? g.W : 0;
+                    lo = min(lo, ix); hi = max(hi, ix);
+                }
+                lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+                __syncthreads();                                         // every thread has read the first exchange
+                if (lane == 0) { ctl.wbb[warp][0] = lo; ctl.wbb[warp][1] = hi; }
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < kTW; ++w) { lo = min(lo, ctl.wbb[w][0]); hi = max(hi, ctl.wbb[w][1]); }
+                xmin = lo; xmax = hi;
+                seam = true;
+            }
+            const int x_org = RAW ? xmin : ((xmin - MX0) & ~3);
+            const int y_org = ymin - MY0 - (seam ? 1 : 0);               // seam: box row j holds row y_org + j up to column W-1, then row y_org + j + 1 from column 0
             const int npx = xmax + MX1 - x_org, rows = ymax + MY1 + 1 - y_org;
             const int gx0 = (3 * x_org) & ~15;                           // TMA: 16-byte aligned byte column
             const int delta = 3 * x_org - gx0;                           // 0, 4, 8 or 12 (RAW: 0 .. 15)
-            const int need = delta + 3 * (npx + 1);                      // bytes of a row the records depend on
-            const int wsel = RAW ? (need + 63) / 64 - 1 : (need + 47) / 48 - 1;   // box width 48 (wsel + 1); RAW: 64 (wsel + 1)
-            const uint32_t bw = (RAW ? 64u : 48u) * (uint32_t)(wsel + 1);
-            // one TMA box per frame: the smallest of the three box heights that covers the footprint
-            const int hsel = max(0, kTNumBoxH - 1 - (a.rows_max - rows) / kTBoxRows);
-            const uint32_t box_rows = (uint32_t)(a.rows_max - kTBoxRows * (kTNumBoxH - 1 - hsel));
+            const int need = delta + 3 * (npx + 1) + (seam ? 8 : 0);     // bytes of a row the records depend on (seam: + the 8-byte straddle strip at the row's end)
+            const int e_a = delta + 3 * (g.W - x_org);                   // seam: where a box row passes column W-1 of its source row
+            // box class: a regular box {64 / 48 (wsel + 1) bytes x one of three heights}, else a wide class (kTNumWide)
+            int tmi = -1;
+            uint32_t bw = RAW ? 64u : 48u, box_rows = 8u;
+            {
+                const int wsel = RAW ? (need + 63) / 64 - 1 : (need + 47) / 48 - 1;
+                const uint32_t bwr = (RAW ? 64u : 48u) * (uint32_t)(wsel + 1);
+                if (rows <= a.rows_max && bwr <= (uint32_t)a.bw_max) {
+                    // one TMA box per frame: the smallest of the three box heights that covers the footprint (seam: the full height)
+                    const int hsel = seam ? kTNumBoxH - 1 : max(0, kTNumBoxH - 1 - (a.rows_max - rows) / kTBoxRows);
+                    bw = bwr;
+                    box_rows = (uint32_t)(a.rows_max - kTBoxRows * (kTNumBoxH - 1 - hsel));
+                    tmi = seam ? kTMapSeam0 + wsel : hsel * kTNumBoxW + wsel;
+                } else if (a.wide_ok) {
+#pragma unroll
+                    for (int c = kTNumWide - 1; c >= 0; --c)
+                        if (need <= tiled_wide_bw(c) && rows <= a.wide_rows[c]) {
+                            bw = (uint32_t)tiled_wide_bw(c); box_rows = (uint32_t)a.wide_rows[c];
+                            tmi = (seam ? kTMapSeam0 + 4 : kTMapWide0) + c;
+                        }
+                }
+            }
             // (coordinates outside [0, W-2] x [0, H-2] mean a wrapped tap: seam or pole)
-            const bool staged = a.stage_ok && xmin - MX0 >= 0 && ymin - MY0 >= 0 && xmax + MX1 <= g.W - 1 &&
-                                ymax + MY1 <= g.H - 1 && rows <= a.rows_max && bw <= (uint32_t)a.bw_max;
+            bool staged = a.stage_ok && tmi >= 0 && ymin - MY0 >= 0 && ymax + MY1 <= g.H - 1;
+            if (seam) staged = staged && y_org >= 0 && y_org + (int)box_rows <= g.H - 1 &&                  // the last box row borrows the row after it
+                               3 * g.W - gx0 <= kTSeamHalf && gx0 + (int)bw - 3 * g.W <= kTSeamHalf;        // inside the seam window
+            else staged = staged && xmin - MX0 >= 0 && xmax + MX1 <= g.W - 1;
+            const bool wide = staged && tmi >= kTMapWide0 && !(seam && tmi < kTMapSeam0 + 4);
             bool generic = !a.aligned;
+            bool deferred = false;
+            if (DEFER && !staged && a.mode == 1) {                       // first launch: leave it to the second one (larger buffers)
+                if (tid == 0) {
+                    const unsigned idx = atomicAdd(a.defer_count, 1u);
+                    const bool took = idx < (unsigned)a.defer_cap;        // (a full list: gather it here after all)
+                    if (took) {
+                        a.defer_list[2 * idx] = (unsigned)item;
+                        a.defer_list[2 * idx + 1] = (unsigned)vi;
+                    }
+                    ctl.def_took = took ? 1 : 0;
+                }
+                __syncthreads();
+                deferred = ctl.def_took != 0;                            // (rewritten only after this view's closing barrier)
+            }
             if (!staged) {                                               // uniform over the CTA
                 bool special = false;
 #pragma unroll
@@ -626,7 +739,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 }
                 generic = (__syncthreads_or(special) != 0) || !a.aligned;
             }
-            if (a.tile_modes && tid == 0 && chunk == 0) atomicAdd(&a.tile_modes[staged ? 0 : (generic ? 2 : 1)], 1u);
+            if (a.tile_modes && tid == 0 && f_begin == 0 && !deferred) atomicAdd(&a.tile_modes[staged ? (seam ? 4 : (wide ? 3 : 0)) : (generic ? 2 : 1)], 1u);
 
             // ---- 3. per-pixel gather state: staged {upper record, lower record, w0x, w1x}, direct {off, wx, wy} --
             // (Lanczos4: contiguous records, 8 B per source pixel, state {record of tap (0, 0), table row offset})
@@ -653,8 +766,14 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     const uint32_t fx = sxs[k] & 31, fy = sys[k] & 31;
                     const uint32_t rx = (uint32_t)((sxs[k] >> 5) - x_org), ry = (uint32_t)((sys[k] >> 5) - y_org);
                     if constexpr (RAW) {
-                        const uint32_t o = (uint32_t)delta + 3u * rx;
-                        pa[k] = raw_s + ry * bw + (o & ~3u);                            // upper record in raw buffer 0; lower: + bw
+                        uint32_t o = (uint32_t)delta + 3u * rx, ryb = ry;
+                        if (seam) {                                                      // columns in unwrapped coordinates
+                            const int ixu = (sxs[k] >> 5) + (((sxs[k] >> 5) < (g.W >> 1)) ? g.W : 0);
+                            o = (uint32_t)delta + 3u * (uint32_t)(ixu - x_org);
+                            if (ixu >= g.W) ryb = ry - 1u;                               // past the seam: the head of the next source row sits one box row up
+                            else if (ixu == g.W - 1) o = bw - 8u;                        // straddles it: the strip [pixel W-1 | pixel 0] built per frame
+                        }
+                        pa[k] = raw_s + ryb * bw + (o & ~3u);                           // upper record in raw buffer 0; lower: + bw
                         pa2[k] = 0; ph[k] = 0; ph2[k] = 0;
                         if (!COLSEL || k == kTP) {
                             const uint32_t al_k = o & 3u;
@@ -696,7 +815,11 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             // source is not minified along y and the source column is constant: most ring / cube tiles.)
             const bool any_a = __any_sync(0xffffffffu, ((pm & ~(3u << (2 * (HC - 1)))) & 0xaaaaaaaau) != 0u);
             // RAW: byte alignment of this thread's source column (the same for its 8 pixels: column-only map_x)
-            const uint32_t al = RAW ? (((uint32_t)delta + 3u * (uint32_t)((sxs[0] >> 5) - x_org)) & 3u) : 0u;
+            uint32_t al = 0u;
+            if (RAW) {
+                const int ix0 = (sxs[0] >> 5) + ((seam && (sxs[0] >> 5) < (g.W >> 1)) ? g.W : 0);
+                al = (seam && ix0 == g.W - 1) ? 0u : (((uint32_t)delta + 3u * (uint32_t)(ix0 - x_org)) & 3u);   // (the strip is word-aligned)
+            }
             uint32_t sel_lo = 0x4130u + 0x1111u * al, sel_hi = ((al + 6u) & 7u) | (((al + 1u) & 7u) << 4);
             uint32_t m3 = al == 3u ? 0xffffffffu : 0u;
             asm volatile("" : "+r"(sel_lo), "+r"(sel_hi), "+r"(m3));
@@ -709,11 +832,17 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             uint32_t tdst0 = off_pairs + (LZ ? 32u : 16u) * tid;                   // records / lo plane; hi plane: off_hi + 8 i
             uint32_t thi0 = off_hi + 8u * tid;
             asm volatile("" : "+r"(tsrc0), "+r"(tdst0), "+r"(thi0));     // hoisted out of the frame loop for good
-            const CUtensorMap *tm = &tms.in[staged ? hsel * kTNumBoxW + wsel : 0];
-            auto issue_box = [&](int f, uint32_t b) {                    // one thread: frame f -> raw buffer b
-                tma_issue_box_s(raw_s + b * raw_bytes, tm, gx0, y_org, f, mbar_s + 8u * b, box_rows * bw);
+            auto issue_box = [&](int f, uint32_t b) {                    // thread 0: frame f -> raw buffer b (box parameters in ctl, its own)
+                tma_issue_box_s(raw_s + b * raw_bytes, &tms.m[ctl.box_map], ctl.box_cx, ctl.box_cy0 + f * ctl.box_cyf, f * ctl.box_czf,
+                                mbar_s + 8u * b, (uint32_t)ctl.box_bytes);
             };
             if (staged && tid == 0) {                                    // NB frames in flight
+                const int cxb = seam ? gx0 - (3 * g.W - kTSeamHalf) : gx0;           // byte column in the frame tensor / the seam window
+                const bool u32 = tmi >= kTMapWide0 && !(seam && tmi < kTMapSeam0 + 4);  // wide classes: uint32 elements
+                ctl.box_cx = u32 ? cxb >> 2 : cxb;
+                ctl.box_cy0 = y_org; ctl.box_cyf = seam ? g.H : 0; ctl.box_czf = seam ? 0 : 1;
+                ctl.box_bytes = (int)(box_rows * bw); ctl.box_map = tmi;
+                ctl.seam_ea = e_a; ctl.seam_rows = rows;
                 uint32_t b = rbn;
 #pragma unroll
                 for (int j = 0; j < NB; ++j, b = (b + 1u == (uint32_t)NB) ? 0u : b + 1u)
@@ -721,13 +850,32 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             }
 
             // ---- 4. walk the frame chunk ---------------------------------------------------------
-            for (int f = f_begin; f < f_end; ++f, ++it) {
+            const int f_lo = deferred ? f_end : f_begin;                 // a deferred pair: no frames here
+            for (int f = f_lo; f < f_end; ++f, ++it) {
                 const uint32_t rb = rbn;
                 if (!RAW || staged) rbn = (rbn + 1u == (uint32_t)NB) ? 0u : rbn + 1u;
                 if (staged) {
                     if constexpr (RAW) {                                  // buffers are used in cyclic order: one parity per round
                         mbar_wait_s(mbar_s + 8u * rb, rpar);
                         if (rbn == 0u) rpar ^= 1u;
+                        if (seam) {                                       // uniform over the CTA
+                            // the straddle strip: box row j gets [pixel W-1 of its source row | pixel 0 of the same row, which
+                            // arrived at the tail of box row j-1] in its last 8 bytes (the box is at least 8 bytes wider than the footprint)
+                            const uint32_t ea = (uint32_t)ctl.seam_ea, base = raw_s + rb * raw_bytes;
+                            for (int j = tid + 1; j < ctl.seam_rows; j += kTT) {
+                                const uint32_t row = base + (uint32_t)j * bw;
+#pragma unroll
+                                for (uint32_t i = 0; i < 3u; ++i) {
+                                    uint32_t p0, p1;
+                                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p0) : "r"(row + ea - 3u + i));
+                                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p1) : "r"(row - bw + ea + i));
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + bw - 8u + i), "r"(p0) : "memory");
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + bw - 5u + i), "r"(p1) : "memory");
+                                }
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the next box will overwrite these bytes
+                            __syncthreads();
+                        }
                     } else {
                     mbar_wait_s(mbar_s + 8u * rb, (phase >> rb) & 1u);
                     phase ^= 1u << rb;
@@ -896,7 +1044,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (a.store_ok) {
                     if (tid == 0) {
                         if (RAW && staged && f + NB < f_end) issue_box(f + NB, rb);
-                        tma_store_tile(&tms.out, RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
+                        tma_store_tile(&tms.m[kTMapOut], RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
                     }
                 } else {
                     if (RAW && staged && f + NB < f_end && tid == 0) issue_box(f + NB, rb);
@@ -924,7 +1072,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 }
             }
             __syncthreads();                           // every warp's partial of the last frame is in
-            if (SCORES && tid == 0) {
+            if (SCORES && tid == 0 && f_lo < f_end) {
                 long long s1 = 0, s2 = 0;
                 int (*const wsum_last)[2] = (RAW && !(it & 1u)) ? reinterpret_cast<int (*)[2]>(dsm + off_wsum2) : ctl.wsum;   // `it` is past the last frame
 #pragma unroll

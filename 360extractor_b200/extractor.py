@@ -30,7 +30,7 @@ def scores_from_sums(sum_lap, sum_lap2, n_pixels: int) -> np.ndarray:
     return s2 / float(n_pixels) - mean * mean
 
 
-def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *, out_h=None):
+def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *, out_h=None, flags=0):
     """Host-only view of how the tiled bilinear path organises a job (no device needed): the view units
     that share one map evaluation (views differing only by a yaw), each view's map_x shift inside its
     unit, and the shared-memory staging capacity chosen from the tiles' source footprints."""
@@ -43,6 +43,7 @@ def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear",
     p.interp = interp_code(interpolation_mode)
     p.n_views = int(R.shape[0])
     p.R = R.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    p.flags = int(flags)
     n_units = ctypes.c_int32()
     rows, bw, th = (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)()
     unit = np.zeros(p.n_views, np.int32)
@@ -65,7 +66,7 @@ class Extractor:
     """Plan wrapper.  ``R`` is fp64 ``[V][3][3]`` from ``GeometryProcessor.get_rotation_matrix``."""
 
     def __init__(self, src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear", *,
-                 out_h=None, device=0, max_batch=0, path=_capi.PATH_AUTO, sharpen_strength=None):
+                 out_h=None, device=0, max_batch=0, path=_capi.PATH_AUTO, sharpen_strength=None, flags=0):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
         self.src_h, self.src_w = int(src_h), int(src_w)
         self.out_w = int(out_res)
@@ -86,6 +87,7 @@ class Extractor:
         p.device = self.device
         p.max_batch = int(max_batch)
         p.path = int(path)
+        p.flags = int(flags)              # FLAG_* overrides of the plan's own choices (include/x360.h); 0 = let the plan choose
         self._plan = ctypes.c_void_p()
         check(lib().x360_plan_create(ctypes.byref(p), ctypes.byref(self._plan)))
         self.sharpen_strength = None
@@ -135,27 +137,38 @@ class Extractor:
         return {"path": vals[0].value, "grid": vals[1].value, "block": vals[2].value, "smem_bytes": vals[3].value}
 
     def tile_modes(self):
-        """Tiles of the last launch per gather mode (synchronises): staged / direct-aligned / direct-bytewise."""
-        out = (ctypes.c_uint32 * 3)()
+        """(tile, view) pairs of the last launch per gather mode (synchronises): staged in a regular TMA box / in a wide
+        box / across the seam, or gathered directly (aligned words / bytes)."""
+        out = (ctypes.c_uint32 * 5)()
         check(lib().x360_plan_tile_modes(self._plan, out))
-        return {"staged": int(out[0]), "direct_aligned": int(out[1]), "direct_bytewise": int(out[2])}
+        return {"staged": int(out[0]), "direct_aligned": int(out[1]), "direct_bytewise": int(out[2]),
+                "staged_wide": int(out[3]), "staged_seam": int(out[4])}
 
     # -- the hot path --------------------------------------------------------------------------
+    def _host_batch(self, frames, out):
+        """Validate a host frame batch and its output buffer (the C side trusts the sizes it is given)."""
+        frames = np.asarray(frames)
+        if frames.dtype != np.uint8:
+            raise TypeError(f"frames must be uint8 (got {frames.dtype}); the reference's frames are always 8-bit BGR")
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim == 3:
+            frames = frames[None]
+        if frames.ndim != 4 or frames.shape[1:] != self.frame_shape:
+            raise ValueError(f"frames shape {frames.shape} does not match plan {self.frame_shape}")
+        F = frames.shape[0]
+        if out is None:
+            out = np.empty(self.views_shape(F), np.uint8)
+        elif not isinstance(out, np.ndarray) or out.shape != self.views_shape(F) or out.dtype != np.uint8 or not out.flags.c_contiguous \
+                or not out.flags.writeable:
+            raise ValueError("out must be a writable C-contiguous uint8 array of shape %r" % (self.views_shape(F),))
+        return frames, out, F
+
     def extract(self, frames, want_scores=False, out=None):
         """frames uint8 ``[F][H][W][3]`` (numpy / pinned numpy) -> ``(views uint8 [F][V][d][d][3], scores)``.
 
         ``scores`` is float64 ``[F][V]`` (or ``None``).  Host buffers: upload, kernels and download
         are pipelined in the library on side streams."""
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
-        if frames.ndim == 3:
-            frames = frames[None]
-        if frames.shape[1:] != self.frame_shape:
-            raise ValueError(f"frames shape {frames.shape} does not match plan {self.frame_shape}")
-        F = frames.shape[0]
-        if out is None:
-            out = np.empty(self.views_shape(F), np.uint8)
-        elif out.shape != self.views_shape(F) or out.dtype != np.uint8 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous uint8 array of shape %r" % (self.views_shape(F),))
+        frames, out, F = self._host_batch(frames, out)
         s = s2 = None
         if want_scores:
             s = np.zeros((F, self.n_views), np.int64)
@@ -166,12 +179,7 @@ class Extractor:
 
     def extract_sums(self, frames, out=None):
         """Like ``extract`` but returns the raw int64 ``(sum L, sum L^2)`` arrays."""
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
-        if frames.ndim == 3:
-            frames = frames[None]
-        F = frames.shape[0]
-        if out is None:
-            out = np.empty(self.views_shape(F), np.uint8)
+        frames, out, F = self._host_batch(frames, out)
         s = np.zeros((F, self.n_views), np.int64)
         s2 = np.zeros((F, self.n_views), np.int64)
         check(lib().x360_extract_host(self._plan, ptr(frames), F, ptr(out), ptr(s), ptr(s2)))

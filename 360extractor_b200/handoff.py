@@ -16,14 +16,19 @@ from ._capi import check, lib, ptr
 
 
 def normalize_mask_faces(ai_mask_cameras):
-    """Per-face mask selection -> lowercase set of face names, or ``None`` = every face
-    (src/core/settings_manager.py:103-116; read at src/core/processor.py:194)."""
-    if not ai_mask_cameras:
-        return None
+    """The ``ai_mask_cameras`` setting as the masker's face filter: ``None`` (every face) when the setting is empty or
+    names nothing, else the named faces as a lowercase set.  Behaviour of src/core/settings_manager.py:103-116 (read at
+    src/core/processor.py:194); a maintainer wiring this into the reference would import that function instead."""
     if isinstance(ai_mask_cameras, str):
-        ai_mask_cameras = ai_mask_cameras.split(",")
-    faces = {str(c).strip().lower() for c in ai_mask_cameras if str(c).strip()}
-    return faces or None
+        tokens = ai_mask_cameras.split(",")
+    else:
+        tokens = list(ai_mask_cameras) if ai_mask_cameras else []
+    names = set()
+    for token in tokens:
+        name = str(token).strip().lower()
+        if name:
+            names.add(name)
+    return names if names else None
 
 
 def eligible_indices(batch_names, mask_face_filter):
@@ -47,16 +52,25 @@ def masker_slots(n_frames, names, ai_mask_cameras=None, keep=None):
     return slots
 
 
-def masker_input(views, names, ai_mask_cameras=None, keep=None, to_rgb=True, out=None, stream=None, device=0):
+def masker_input(views, names, ai_mask_cameras=None, keep=None, to_rgb=True, out=None, stream=None, device=None):
     """Device views -> ``(slots, tensor)``.
 
     ``views``: torch CUDA uint8 ``[F][V][d][d][3]`` (what ``Extractor.extract_device`` filled);
     ``tensor``: torch CUDA float32 ``[len(slots)][3][d][d]``, ``v / 255``, RGB unless ``to_rgb=False``.
-    Nothing crosses PCIe; asynchronous on ``stream`` (default: the current torch stream)."""
+    Nothing crosses PCIe; asynchronous on ``stream`` (default: the current torch stream).  The kernel runs on the
+    device that holds ``views`` (``device`` is only checked against it).
+
+    Scope: this is tensor plumbing.  It does NOT reproduce the masker's own pre-processing — Ultralytics letterboxes each
+    image to the model's ``imgsz`` inside ``self.model(images, ...)`` (src/core/ai_model.py:145), a third-party step that is
+    absent from this container and therefore unpinned; feed it the sharpened views when sharpening is on, as the reference
+    does (src/core/processor.py:379-383)."""
     import torch
     if views.dtype != torch.uint8 or views.dim() != 5 or views.shape[-1] != 3 or not views.is_cuda or not views.is_contiguous():
         raise ValueError("views must be a contiguous CUDA uint8 tensor [F][V][h][w][3]")
     F, V, h, w, _ = (int(x) for x in views.shape)
+    dev_index = views.device.index if views.device.index is not None else torch.cuda.current_device()
+    if device is not None and int(device) != dev_index:
+        raise ValueError(f"views live on cuda:{dev_index}, not on device {device}")
     if len(names) != V:
         raise ValueError(f"{len(names)} names for {V} views")
     slots = masker_slots(F, names, ai_mask_cameras, keep)
@@ -67,8 +81,12 @@ def masker_input(views, names, ai_mask_cameras=None, keep=None, to_rgb=True, out
     if slots:
         sel = np.asarray(slots, dtype=np.int32)
         st = stream if stream is not None else torch.cuda.current_stream(views.device)
-        check(lib().x360_views_to_nchw(int(device), ptr(views), F * V, h, w, sel.ctypes.data, len(slots), 1 if to_rgb else 0,
-                                       ptr(out), getattr(st, "cuda_stream", st)))
+        prev = torch.cuda.current_device()                       # the library selects its device; leave torch's as it was
+        try:
+            check(lib().x360_views_to_nchw(dev_index, ptr(views), F * V, h, w, sel.ctypes.data, len(slots), 1 if to_rgb else 0,
+                                           ptr(out), getattr(st, "cuda_stream", st)))
+        finally:
+            torch.cuda.set_device(prev)
     return slots, out
 
 

@@ -20,7 +20,7 @@ import numpy as np
 from .blur_filter import BlurFilter
 from .extractor import Extractor
 from .geometry import GeometryProcessor, rotation_stack
-from .sharding import gather_sums, shard_bounds
+from .sharding import gather_sums, gather_sums_by_view, shard_axis, shard_bounds
 
 
 @dataclass
@@ -48,6 +48,12 @@ class ExtractionSession:
         self.sharpen_enabled = settings.get("sharpening_enabled", False)   # processor.py:228
         self.sharpen_strength = settings.get("sharpening_strength", 0.5)   # processor.py:229
         self.device = int(device)
+        self._max_batch = int(max_batch)
+        # flat (non-360) media are passed through untouched by the reference (processor.py:336-338: one "Flat" view =
+        # frame.copy()); there is nothing to reproject, so this session refuses them instead of reprojecting silently
+        if not settings.get("is_360", True):
+            raise ValueError("ExtractionSession reprojects 360 media; settings['is_360'] is False (flat media are copied "
+                             "through by the reference, src/core/processor.py:336-338 — no GPU path is needed for that)")
         self.views = GeometryProcessor.generate_views(camera_count, pitch_offset=pitch_offset, layout_mode=layout_mode)
         self.active_cameras = settings.get("active_cameras", None)      # job.py:12
         self.names, R = rotation_stack(self.views, self.active_cameras)
@@ -64,6 +70,10 @@ class ExtractionSession:
         if self.extractor is not None:
             self.extractor.close()
             self.extractor = None
+        if getattr(self, "_vs_extractor", None) is not None:
+            self._vs_extractor.close()
+            self._vs_extractor = None
+            self._vs_key = None
 
     def __enter__(self):
         return self
@@ -93,7 +103,9 @@ class ExtractionSession:
         """Frame-sharded variant: this rank reprojects frames ``shard_bounds(F, world, rank)``, the
         score sums are all-gathered and every rank replays the blur machine over the full table.
 
-        Returns ``(lo, local_views, keep)`` with ``keep`` a bool ``[F][V]`` table valid on every rank."""
+        Returns ``(lo, local_views, keep)`` with ``keep`` a bool ``[F][V]`` table valid on every rank.
+        Jobs with fewer frames than ranks (single images) are sharded by view instead: see
+        ``process_view_sharded``."""
         F = len(frames)
         lo, hi = shard_bounds(F, world_size, rank)
         local = np.ascontiguousarray(frames[lo:hi])
@@ -111,6 +123,56 @@ class ExtractionSession:
         scores = scores_from_sums(gs, gs2, self.extractor.pixels_per_view)
         keep = np.array(self.blur.replay(scores), dtype=bool).reshape(F, V)
         return lo, views, keep
+
+    def _view_shard_extractor(self, v_lo: int, v_hi: int):
+        """A plan over this rank's block of the emitted views (same frame size, same settings)."""
+        key = (v_lo, v_hi)
+        if getattr(self, "_vs_key", None) != key:
+            if getattr(self, "_vs_extractor", None) is not None:
+                self._vs_extractor.close()
+            _, R = rotation_stack(self.views, self.active_cameras)
+            self._vs_extractor = Extractor(self.src_h, self.src_w, self.out_res, self.fov, R[v_lo:v_hi], self.interpolation_mode,
+                                           device=self.device, max_batch=self._max_batch,
+                                           sharpen_strength=self.sharpen_strength if self.sharpen_enabled else None)
+            self._vs_key = key
+        return self._vs_extractor
+
+    def process_view_sharded(self, frames, rank: int, world_size: int, group=None):
+        """View-sharded variant for jobs with fewer frames than GPUs (a single 360 image: the loop of
+        src/core/processor.py:327-330 is what gets split): this rank reprojects EVERY frame for the views
+        ``shard_bounds(V, world, rank)`` of the emitted view list; sums are all-gathered along the view axis and
+        the blur machine is replayed in (frame, view) order on every rank.
+
+        Returns ``(v_lo, local_views [F][V_local][d][d][3], keep [F][V])``."""
+        F, V = len(frames), len(self.names)
+        v_lo, v_hi = shard_bounds(V, world_size, rank)
+        frames = np.ascontiguousarray(frames)
+        if v_hi == v_lo:
+            views = np.empty((F, 0, self.out_res, self.out_res, 3), np.uint8)
+            s = s2 = np.zeros((F, 0), np.int64)
+        else:
+            ex = self._view_shard_extractor(v_lo, v_hi)
+            if self.blur.enabled:
+                views, s, s2 = ex.extract_sums(frames)
+            else:
+                views, s, s2 = ex.extract(frames)[0], None, None
+        if not self.blur.enabled:
+            return v_lo, views, np.ones((F, V), bool)
+        gs, gs2 = gather_sums_by_view(s, s2, V, group=group)
+        from .extractor import scores_from_sums
+        scores = scores_from_sums(gs, gs2, self.out_res * self.out_res)
+        keep = np.array(self.blur.replay(scores), dtype=bool).reshape(F, V)
+        return v_lo, views, keep
+
+    def process_distributed(self, frames, rank: int, world_size: int, group=None):
+        """Pick the sharding axis: frames when there are at least as many as ranks, else views.
+        Returns ``(axis, lo, local_views, keep)``."""
+        axis = shard_axis(len(frames), world_size)
+        if axis == "frame":
+            lo, views, keep = self.process_sharded(frames, rank, world_size, group=group)
+        else:
+            lo, views, keep = self.process_view_sharded(frames, rank, world_size, group=group)
+        return axis, lo, views, keep
 
 
 __all__ = ["ExtractionSession", "ViewResult"]

@@ -1,10 +1,13 @@
-"""Frame sharding across the GPUs of one box.
+"""Sharding across the GPUs of one box: by frame, or — for jobs with fewer frames than GPUs — by view.
 
-Every (frame, view, tile) is independent, so frames are split into contiguous index blocks, one
-per rank, with no pixel traffic between GPUs.  The only exchange is the per-view blur score:
-the accept/reject machine of src/core/processor.py:345-367 is sequential over (frame, view), so
-the int64 sum pairs are all-gathered (a few KB, NCCL on GPUs / gloo in the CPU tests) and every
-rank replays the machine over the full, ordered score table.
+Every (frame, view, tile) is independent, so the work is split into contiguous index blocks, one
+per rank, with no pixel traffic between GPUs: frames of the sampled frame list (after the
+``frame_idx % interval`` gate, src/core/processor.py:286), or the views of the per-frame loop
+(src/core/processor.py:327-330) when a job is a single image (every rank then uploads the same
+frame; nothing is broadcast).  The only exchange is the per-view blur score: the accept/reject
+machine of src/core/processor.py:345-367 is sequential over (frame, view), so the int64 sum pairs
+are all-gathered (a few KB, NCCL on GPUs / gloo in the CPU tests) and every rank replays the
+machine over the full, ordered score table.
 """
 from __future__ import annotations
 
@@ -22,6 +25,20 @@ def shard_bounds(n_items: int, world_size: int, rank: int):
 
 def shard_sizes(n_items: int, world_size: int):
     return [shard_bounds(n_items, world_size, r)[1] - shard_bounds(n_items, world_size, r)[0] for r in range(world_size)]
+
+
+def shard_axis(n_frames: int, world_size: int) -> str:
+    """'frame' when every rank can get at least one frame, else 'view' (single-image jobs)."""
+    return "frame" if n_frames >= world_size else "view"
+
+
+def gather_sums_by_view(sum_lap, sum_lap2, n_views_total: int, group=None):
+    """View-sharded counterpart of ``gather_sums``: every rank holds ``[F][V_local]`` for its view block
+    (``shard_bounds(V, world, rank)``); returns the full ``[F][V]`` tables on every rank."""
+    import torch
+    t = (lambda a: a.transpose(0, 1).contiguous()) if torch.is_tensor(sum_lap) else (lambda a: np.ascontiguousarray(np.asarray(a).T))
+    s, s2 = gather_sums(t(sum_lap), t(sum_lap2), n_views_total, group=group)
+    return np.ascontiguousarray(s.T), np.ascontiguousarray(s2.T)
 
 
 def gather_sums(sum_lap, sum_lap2, n_frames_total: int, group=None):
@@ -67,4 +84,4 @@ def _to_numpy(a):
     return np.asarray(a)
 
 
-__all__ = ["shard_bounds", "shard_sizes", "gather_sums"]
+__all__ = ["shard_bounds", "shard_sizes", "shard_axis", "gather_sums", "gather_sums_by_view"]

@@ -35,9 +35,19 @@ def unsharp_mask(images, strength=0.5, device=0, out=None):
     return out[0] if single else out
 
 
-def unsharp_mask_device(images, out, strength=0.5, device=0, stream=None):
+def _device_of(t, device):
+    """CUDA ordinal of a torch tensor (``device`` = explicit override for raw pointers); restores nothing itself."""
+    idx = getattr(getattr(t, "device", None), "index", None)
+    if idx is None:
+        return 0 if device is None else int(device)
+    if device is not None and int(device) != idx:
+        raise ValueError(f"tensor lives on cuda:{idx}, not on device {device}")
+    return int(idx)
+
+
+def unsharp_mask_device(images, out, strength=0.5, device=None, stream=None):
     """Device-resident batch (torch CUDA uint8 tensors ``[N][h][w][3]``, ``out`` distinct from ``images``);
-    asynchronous on ``stream``."""
+    asynchronous on ``stream``; runs on the device that holds ``images``."""
     if tuple(images.shape) != tuple(out.shape) or len(images.shape) != 4 or images.shape[3] != 3:
         raise ValueError("images / out must both be [N][h][w][3]")
     for name, t in (("images", images), ("out", out)):
@@ -45,4 +55,15 @@ def unsharp_mask_device(images, out, strength=0.5, device=0, stream=None):
             raise ValueError(f"{name} must be C-contiguous")
     st = getattr(stream, "cuda_stream", stream) if stream is not None else None
     n, h, w, _ = (int(v) for v in images.shape)
-    check(lib().x360_unsharp_device(int(device), ptr(images), n, h, w, float(strength), ptr(out), st))
+    dev = _device_of(images, device)
+    prev = None
+    try:
+        import torch
+        prev = torch.cuda.current_device() if torch.cuda.is_available() else None
+    except ImportError:
+        pass
+    try:
+        check(lib().x360_unsharp_device(dev, ptr(images), n, h, w, float(strength), ptr(out), st))
+    finally:
+        if prev is not None and prev != dev:
+            torch.cuda.set_device(prev)

@@ -41,8 +41,8 @@ extern "C" {
 
 /* kernel-path selector (x360_params.path): 0 lets the plan choose */
 #define X360_PATH_AUTO    0
-#define X360_PATH_DIRECT  1   /* taps gathered straight from global/L2 through L1 */
-#define X360_PATH_STAGED  2   /* the earlier staged bilinear kernel (kept as a comparison path) */
+#define X360_PATH_DIRECT  1   /* taps gathered straight from global/L2 through L1   (comparison path: only in libraries */
+#define X360_PATH_STAGED  2   /* the first staged bilinear kernel                    built with -DX360_LAB; X360_E_UNSUPPORTED otherwise) */
 #define X360_PATH_TILED   3   /* TMA in / pair records / dp2a gather / TMA out, maps shared across yaw-shifted views
                                  (bilinear and Lanczos4; what AUTO resolves to) */
 
@@ -68,8 +68,17 @@ typedef struct x360_params {
     int32_t max_batch;        /* frames per pipelined chunk in x360_extract_host (0 = default 2: small chunks keep both
                                  PCIe directions busy; the kernel is far from being the bottleneck there) */
     int32_t path;             /* X360_PATH_* */
-    int32_t reserved;
+    int32_t flags;            /* X360_FLAG_* overrides of the plan's own choices (0 = let the plan choose) */
 } x360_params;
+
+/* x360_params.flags: explicit overrides of what the plan would choose by itself (every variant computes the same bytes;
+ * the parity suite runs each one).  The library reads no environment variable unless it is built with -DX360_LAB. */
+#define X360_FLAG_PLANES       1   /* bilinear: pair-record planes (transform pass) instead of the raw gather */
+#define X360_FLAG_FUSED_SCORE  2   /* blur score fused into the extraction kernel (tile + 1-px halo) */
+#define X360_FLAG_SPLIT_SCORE  4   /* blur score by one streaming pass over the finished views */
+#define X360_FLAG_TILE_H16     8   /* 32 x 16 output tiles */
+#define X360_FLAG_TILE_H32    16   /* 32 x 32 output tiles */
+#define X360_FLAG_NO_WIDE     32   /* no wide / seam boxes: tiles beyond the regular staging capacity take the direct gathers */
 
 int x360_plan_create(const x360_params *params, x360_plan **out_plan);
 int x360_plan_destroy(x360_plan *plan);
@@ -201,10 +210,10 @@ int64_t x360_launch_count(void);
 /* which path the plan's extract kernel uses (X360_PATH_*), and its launch geometry */
 int x360_plan_info(const x360_plan *plan, int32_t *path, int32_t *grid, int32_t *block, int32_t *smem_bytes);
 
-/* tiles of the LAST extract launch per gather mode: [0] staged in shared memory,
- * [1] direct aligned-word gather, [2] direct byte-wise gather (seam / pole / odd geometry).
- * Synchronises the device. */
-int x360_plan_tile_modes(x360_plan *plan, uint32_t *out3);
+/* (tile, view) pairs of the LAST extract launch per gather mode: [0] staged in shared memory by one regular TMA box,
+ * [1] direct aligned-word gather, [2] direct byte-wise gather (pole rows / odd geometry), [3] staged by a wide box
+ * (footprints near the poles), [4] staged across the +-pi seam.  Synchronises the device. */
+int x360_plan_tile_modes(x360_plan *plan, uint32_t *out5);
 
 #ifdef __cplusplus
 }

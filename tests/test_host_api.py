@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_json, unhex
+from conftest import GOLDEN, ROOT, load_json, unhex
 
 
 # ---- reference tests/test_core.py:18-65, transposed onto the drop-in -------------------------
@@ -295,3 +295,49 @@ def test_mask_face_selection_mirrors_reference(x360):
     assert x360.masker_slots(1, names) == [0, 1, 2, 3, 4, 5]
     res = x360.scatter_results([4, 5], [("imgU", "maskU"), ("imgD", "maskD")], [f"img{i}" for i in range(6)])
     assert res[0] == ("img0", None) and res[4] == ("imgU", "maskU") and res[5] == ("imgD", "maskD") and len(res) == 6
+
+
+# ---- the caller contract pinned to the reference's own loop (tests/golden/make_worker_golden.py) ----------------------
+def _worker_cases():
+    import json
+    with open(os.path.join(GOLDEN, "worker_cases.json")) as f:
+        return json.load(f)
+
+
+def worker_expectations(x360, case):
+    """(names of the emitted views, reference scores [F][V] or None, kept (frame, camera) pairs) of one recorded scenario."""
+    st = case["settings"]
+    layout = "ring" if st["layout_mode"] == "adaptive" else st["layout_mode"]
+    views = x360.GeometryProcessor.generate_views(st["camera_count"], pitch_offset=st["pitch_offset"], layout_mode=layout)
+    names, _ = x360.rotation_stack(views, st.get("active_cameras"))
+    scores = [float.fromhex(h) for h in case["scores_in_call_order"]]
+    table = np.array(scores).reshape(-1, len(names)) if scores else None
+    kept = []
+    for fn in case["kept"]:                                    # clip_frame000003_View_2.png (processor.py:446)
+        stem = fn[: -len(".png")]
+        frame, cam = stem[len("clip_frame"):].split("_", 1)
+        kept.append((int(frame), cam))
+    order = {n: i for i, n in enumerate(names)}
+    kept.sort(key=lambda fc: (fc[0], order[fc[1]]))
+    return names, table, kept
+
+
+@pytest.mark.parametrize("name", ["smart_ring4", "plain_threshold_cube", "smart_active_cameras", "filter_off_fibonacci",
+                                  "smart_sharpened_lanczos", "legacy_adaptive_layout"])
+def test_blur_machine_reproduces_the_reference_worker(x360, name):
+    """BlurFilter.replay over the scores the REAL ProcessingWorker computed (recorded in call order) keeps exactly the files
+    the worker wrote: threshold rejections, rolling-average rejections and forced accepts (processor.py:341-376)."""
+    case = _worker_cases()["scenarios"][name]
+    names, table, kept = worker_expectations(x360, case)
+    filt = x360.BlurFilter.from_settings(case["settings"])
+    n_frames = _worker_cases()["clip"]["frames"]
+    if table is None:
+        assert not filt.enabled
+        want = [(f, n) for f in range(n_frames) for n in names]
+    else:
+        assert table.shape == (n_frames, len(names))            # one score per (frame, emitted view), in loop order
+        keep = filt.replay(table)
+        want = [(f, names[v]) for f in range(n_frames) for v in range(len(names)) if keep[f][v]]
+    assert want == kept
+    if "smart" in name or "legacy" in name:
+        assert filt.forced >= 1 and filt.skipped >= 1

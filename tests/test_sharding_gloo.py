@@ -79,3 +79,33 @@ def test_gather_without_process_group_is_identity(x360):
     s, s2 = _synthetic_sums(4, 3, 100)
     gs, gs2 = x360.gather_sums(s, s2, 4)
     assert np.array_equal(gs, s) and np.array_equal(gs2, s2)
+
+
+def _view_worker(rank, world, port, F, V, npix, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module("360extractor_b200")
+    s, s2 = _synthetic_sums(F, V, npix)
+    lo, hi = pkg.shard_bounds(V, world, rank)                     # this rank's block of the VIEW list
+    gs, gs2 = pkg.gather_sums_by_view(s[:, lo:hi].copy(), s2[:, lo:hi].copy(), V)
+    keep = np.array(pkg.BlurFilter(True, True, 100.0).replay(pkg.scores_from_sums(gs, gs2, npix)), dtype=bool)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), gs=gs, gs2=gs2, keep=keep)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,F,V", [(2, 1, 5), (3, 2, 4), (3, 1, 2)])
+def test_view_sharded_gather_for_single_frame_jobs(x360, tmp_path, world, F, V):
+    """Fewer frames than ranks (a single 360 image): views are sharded instead; ragged blocks, and with
+    V < world a rank without any view still takes part in the collective."""
+    assert x360.shard_axis(F, world) == "view" and x360.shard_axis(world, world) == "frame"
+    npix = 48 * 48
+    mp.spawn(_view_worker, args=(world, _free_port(), F, V, npix, str(tmp_path)), nprocs=world, join=True)
+    s, s2 = _synthetic_sums(F, V, npix)
+    want_keep = np.array(x360.BlurFilter(True, True, 100.0).replay(x360.scores_from_sums(s, s2, npix)), dtype=bool)
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        assert np.array_equal(z["gs"], s) and np.array_equal(z["gs2"], s2), f"rank {r} gathered table"
+        assert np.array_equal(z["keep"], want_keep), f"rank {r} keep table"
