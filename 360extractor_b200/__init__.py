@@ -16,6 +16,7 @@ from .extractor import Extractor, PinnedBuffer, column_only_map_x, plan_preview,
 from .geometry import GeometryProcessor, focal_length, rotation_stack
 from .handoff import eligible_indices, masker_input, masker_slots, normalize_mask_faces, scatter_results
 from .image_utils import ImageUtils
+from .jpeg import JpegEncoder, encode_jpeg, jpeg_header
 from .pipeline import ExtractionSession, ViewResult
 from .sharding import gather_sums, gather_sums_by_view, shard_axis, shard_bounds, shard_sizes
 from .sharpen import unsharp_mask, unsharp_mask_device
@@ -25,6 +26,7 @@ __version__ = "0.1.0"
 __all__ = [
     "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "BlurAnalyzer",
     "PinnedBuffer", "column_only_map_x", "plan_preview", "remap", "unsharp_mask", "unsharp_mask_device", "scores_from_sums", "rotation_stack", "focal_length",
+    "JpegEncoder", "encode_jpeg", "jpeg_header",
     "gather_sums", "gather_sums_by_view", "shard_axis", "shard_bounds", "shard_sizes",
     "normalize_mask_faces", "eligible_indices", "masker_slots", "masker_input", "scatter_results",
     "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",

@@ -58,6 +58,16 @@ SYMBOLS = {
     "x360_lanczos4_table": (ctypes.c_int, [_vp]),
     "x360_focal": (_dbl, [_i32, _dbl]),
     "x360_plan_preview": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(_i32), _vp, _vp, _vp, _vp, _vp]),
+    "x360_plan_preview_views": (ctypes.c_int, [ctypes.POINTER(Params), _vp, _vp]),
+    "x360_jpeg_create": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
+    "x360_jpeg_destroy": (ctypes.c_int, [_vp]),
+    "x360_jpeg_max_bytes": (_i64, [_vp, _i32]),
+    "x360_jpeg_encode_device": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "x360_jpeg_status": (ctypes.c_int, [_vp, _vp]),
+    "x360_jpeg_encode_host": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "x360_jpeg_coefficients_host": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
+    "x360_jpeg_header": (ctypes.c_int, [_i32, _i32, _i32, _vp, _i32]),
+    "x360_extract_host_jpeg": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "x360_host_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp)]),
     "x360_host_free": (ctypes.c_int, [_vp]),
     "x360_last_error": (ctypes.c_char_p, []),

@@ -19,6 +19,8 @@
 
 #include "x360_common.cuh"
 #include "x360_extract.cuh"
+#include "x360_jpeg.cuh"
+#include "x360_jpeg_tables.hpp"
 #include "x360_lanczos.cuh"
 #include "x360_linear.cuh"
 #include "x360_misc.cuh"
@@ -31,7 +33,7 @@ using namespace x360;
 
 namespace {
 
-constexpr int kRingSlots = 64, kRingWords = 8;
+constexpr int kRingSlots = 64, kRingWords = 16;
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
@@ -187,16 +189,14 @@ PlanOpts plan_opts(int flags)
     o.no_wide = (flags & X360_FLAG_NO_WIDE) != 0 || lab_int("X360_NO_WIDE", 0) != 0;
     return o;
 }
-// Score policy.  The fused score (gray tile + 1-px halo inside the extraction kernel) is what a plan runs unless told
-// otherwise; with X360_FLAG_PLANES it rides on the pair-record planes, else on the raw gather.
-bool score_is_split(const PlanOpts &o) { return o.score_mode == 2; }
+// Score policy.  By default the blur score is a second, streaming pass over the finished views (blur_sums_march_kernel: warp
+// shuffles for the neighbours, block reduction, one atomic pair per CTA): measured on cfg4 (B200) 2.40 ms per 32 frames against
+// 2.87 ms with the score fused into the extraction kernel — the 1-px halo of every 32 x 16 tile costs more than re-reading
+// 3 B / pixel.  X360_FLAG_FUSED_SCORE selects the fused form (on the raw gather; with X360_FLAG_PLANES on the planes).
+bool score_is_split(const PlanOpts &o) { return o.score_mode != 1; }
 // The raw gather (no transform, x360_tiled.cuh RAW) serves every bilinear launch except the ones forced onto the
-// planes; by default the fused score still rides on the planes (measured faster in round 1: cfg4 246 vs 228 Gpix/s).
-bool tiled_raw(bool scores, bool lanczos, const PlanOpts &o)
-{
-    if (lanczos || o.planes) return false;
-    return !scores || o.score_mode == 1;
-}
+// planes (Lanczos4 has its own record layout).
+bool tiled_raw(bool, bool lanczos, const PlanOpts &o) { return !lanczos && !o.planes; }
 
 #ifndef X360_RAW_MINB
 #define X360_RAW_MINB 8       // register allocation target of the 32x32 column-only raw gather: 64 registers, no spills (7 CTAs/SM fit the shared memory; measured +1 % over the 72-register build)
@@ -459,9 +459,11 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
                     for (int c = 0; c < kTNumWide; ++c)
                         if (ft.need <= tiled_wide_bw(c) && ft.rows <= wr[c]) { ++fit_wide; break; }
                 }
-                // cost per tile: 1 in a regular box, ~1.5 in a wide one (a larger box per pixel), 3 through the direct gathers
+                // cost per tile: 1 in a regular box, 3 otherwise.  Wide boxes and the second launch take most of the rest off the
+                // direct path, but measured (cfg1, cfg4) they do not pay for a larger capacity: a cube plan runs 11 % faster
+                // with 32-row buffers than with 40-row ones at the same 7 CTAs/SM, so the capacity is chosen for the regular tiles.
                 const double n = (double)(total ? total : 1);
-                const double cost = ((double)fit + 1.5 * (double)fit_wide + 3.0 * (double)(total - fit - fit_wide)) / n;
+                const double cost = ((double)fit + 3.0 * (double)(total - fit)) / n;
                 const double score = th_factor * occ_factor[occ] / cost;
                 if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; best_th = th; best_unfit = (long long)(total - fit - fit_wide); }
             }
@@ -474,6 +476,41 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
 
 }  // namespace
 
+struct x360_jpeg;
+
+// tensor maps of the last (frames, batch, out) buffer triple per variant: re-encoded only when a pointer changes
+struct MapCache {
+    const void *frames = nullptr; const void *out = nullptr; int n_frames = 0;
+    int stage_ok = 0, store_ok = 0; bool wide_ok = false, seam_ok = false;
+    TiledMaps tms;
+};
+
+// A plan's views are served by one or two GROUPS, each with its own kernel variant, tile height, staging capacity and
+// launch: the views whose map_x does not depend on the output row (yaw-only rotations: every view of a ring at pitch 0, the
+// four horizontal faces of a cube) take the column-only raw gather (32 x 32 tiles, per-thread selectors, 7 CTAs/SM); the
+// others (pole faces, inclined or fibonacci views) the general one.  A cube used to run all six faces through the general
+// variant because two of them need it.
+struct TiledGroup {
+    int n_views = 0;
+    bool col_u0 = false;                 // map_x depends on the output column only (yaw-only rotations)
+    int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with fused scores
+    bool t_raw[2] = {false, false};      // the launch takes the raw-gather variant (no transform)
+    size_t t_smem[2] = {0, 0};           // dynamic shared memory without / with fused scores
+    int grid_cap[2] = {0, 0};            // SMs x resident CTAs (occupancy query at creation)
+    int wide_rows[2][kTNumWide] = {};
+    MapCache maps[2], maps2[2];
+    // second launch (x360_tiled.cuh, TiledArgs::mode): larger staging buffers for the (tile, view) pairs the first launch defers
+    bool two_launch[2] = {false, false};
+    int t2_rows[2] = {0, 0}, t2_bw[2] = {0, 0}, wide_rows2[2][kTNumWide] = {}, grid_cap2[2] = {0, 0};
+    size_t t2_smem[2] = {0, 0};
+    // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit, GLOBAL view indices): a launch takes the
+    // coarsest one that still yields enough work items without cutting the frame batch into chunks
+    int n_units[4] = {0, 0, 0, 0};
+    TiledUnit *d_units[4] = {};
+    int *d_unit_view[4] = {};
+    double *d_unit_shift[4] = {};
+};
+
 struct x360_plan {
     x360_params p;
     Geom g;
@@ -483,40 +520,23 @@ struct x360_plan {
     int path = X360_PATH_DIRECT;        // resolved path of the extraction kernel
     int px_max = 0, rows_max = 0, pp = 0, raw_pitch = 0;
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
-    // Per-launch device scratch: a ring of kRingSlots x 8 words — [0..4] tile-mode counters, [5] the dynamic scheduler's
-    // work-item counter — so launches in flight on different streams never share a counter.
+    // Per-launch device scratch: a ring of kRingSlots x kRingWords words — [0..4] tile-mode counters, [5..8] the work-item
+    // counters of up to four kernel launches of one extract call (two groups x two launches) — so calls in flight on different
+    // streams never share a counter.
     unsigned *d_modes = nullptr;
     int ring_next = 0, ring_last = 0;
     PlanOpts opts;
-    int grid_cap[2] = {0, 0};            // SMs x resident CTAs of the tiled kernel without / with scores (occupancy query at creation)
-    int wide_rows[2][kTNumWide] = {};
-    // tensor maps of the last (frames, batch, out) buffer triple per variant: re-encoded only when a pointer changes
-    struct MapCache {
-        const void *frames = nullptr; const void *out = nullptr; int n_frames = 0;
-        int stage_ok = 0, store_ok = 0; bool wide_ok = false, seam_ok = false;
-        TiledMaps tms;
-    } maps[2], maps2[2];
-    // second launch (x360_tiled.cuh, TiledArgs::mode): larger staging buffers for the (tile, view) pairs the first launch defers
-    bool two_launch[2] = {false, false};
-    int t2_rows[2] = {0, 0}, t2_bw[2] = {0, 0}, wide_rows2[2][kTNumWide] = {}, grid_cap2[2] = {0, 0};
-    size_t t2_smem[2] = {0, 0};
+    TiledGroup grp[2];
+    int n_groups = 0;
+    std::vector<int> view_group;         // group of each view
     static constexpr int kDeferBufs = 4;
     unsigned *d_defer[kDeferBufs] = {};  // [2 defer_cap] entries + [1] count each
     cudaEvent_t defer_ev[kDeferBufs] = {};
     bool defer_used[kDeferBufs] = {};
     int defer_cap = 0, defer_next = 0;
-    // tiled path
-    bool col_u0 = false;                 // map_x depends on the output column only (yaw-only rotations)
-    int t_bw[2] = {144, 144}, t_rows[2] = {40, 40}, t_th[2] = {32, 32};   // staging capacity, tile height (32 or 16), without / with scores
-    bool t_raw[2] = {false, false};      // the launch takes the raw-gather variant (no transform)
     bool split_score = false;            // scores by a separate pass over the finished views instead of the fused reduction
-    // view-unit tables at four granularities (at most 8, 4, 2, 1 views per unit): a launch takes the
-    // coarsest one that still yields enough work items without cutting the frame batch into chunks
-    int n_units[4] = {0, 0, 0, 0};
-    size_t t_smem[2] = {0, 0};           // dynamic shared memory without / with scores
-    TiledUnit *d_units[4] = {};
-    int *d_unit_view[4] = {};
-    double *d_unit_shift[4] = {};
+    cudaStream_t s_side = nullptr;       // the second group's launches run beside the first group's (forked from / joined to the caller's stream)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // pipelined host path
     int chunk = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
@@ -526,21 +546,28 @@ struct x360_plan {
     double sharpen_strength = 0.5;
     long long *d_sums[2] = {};
     bool pipe_ready = false;
+    // encoded host path (x360_extract_host_jpeg): the chunk's views are JPEG-encoded on the device, only the files come back
+    x360_jpeg *jpeg = nullptr;
+    uint8_t *d_jpeg[2] = {};
+    long long *d_joff[2] = {}, *h_joff[2] = {};
+    long long jpeg_cap = 0;
+    cudaStream_t s_off = nullptr;
+    cudaEvent_t ev_off[2] = {};
 };
 
-static int tiled_occupancy(const x360_plan *pl, int sc, size_t smem)
+static int tiled_occupancy(const x360_plan *pl, const TiledGroup &G, int sc, size_t smem)
 {
     int occ = 0;
     const bool lz = pl->p.interp == X360_INTERP_LANCZOS4;
-    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(sc != 0, lz, pl->t_th[sc], pl->col_u0, pl->t_raw[sc]),
-                                                                        32 * tiled_warps(sc != 0, pl->t_th[sc]), smem);
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_tiled(sc != 0, lz, G.t_th[sc], G.col_u0, G.t_raw[sc]),
+                                                                        32 * tiled_warps(sc != 0, G.t_th[sc]), smem);
     if (e != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
     return occ;
 }
 
 static int plan_grid(const x360_plan *pl, bool scores)
 {
-    if (pl->path == X360_PATH_TILED) return pl->grid_cap[scores && !pl->split_score ? 1 : 0];   // capped by the item count at launch
+    if (pl->path == X360_PATH_TILED) return pl->grp[0].grid_cap[scores && !pl->split_score ? 1 : 0];   // capped by the item count at launch
 #ifdef X360_LAB
     int occ = 0;
     cudaError_t e;
@@ -559,22 +586,24 @@ static int plan_grid(const x360_plan *pl, bool scores)
 
 // Tensor maps of a (frames, batch size, out) triple at one staging capacity: encoded when the triple changes and kept
 // (the pipelined host path alternates between two triples; a device-resident caller usually has one).
-static const x360_plan::MapCache *tiled_maps(x360_plan *pl, x360_plan::MapCache &mc, const uint8_t *frames, int n_frames, uint8_t *out_views, int sc,
-                                             int t_rows, const int *wide_rows)
+static const MapCache *tiled_maps(x360_plan *pl, const TiledGroup &G, MapCache &mc, const uint8_t *frames, int n_frames, uint8_t *out_views, int sc,
+                                  int t_rows, const int *wide_rows)
 {
     if (mc.frames == frames && mc.out == out_views && mc.n_frames == n_frames) return &mc;
     const Geom &g = pl->g;
-    const int t_th = pl->t_th[sc];
+    const int t_th = G.t_th[sc];
     mc.frames = nullptr;                               // invalid until the encode below has succeeded
     mc.stage_ok = ((uintptr_t)frames % 16 == 0) && (((size_t)g.W * 3) % 16 == 0) && g.H >= t_rows && g.W * 3 >= 256;
     mc.store_ok = ((uintptr_t)out_views % 16 == 0) && (((size_t)g.ow * 3) % 16 == 0) && g.ow >= kTile && g.oh >= t_th;
     if (lab_int("X360_NO_TMA_STORE", 0)) mc.store_ok = 0;
     mc.wide_ok = mc.stage_ok && !pl->opts.no_wide;
-    mc.seam_ok = mc.wide_ok && pl->t_raw[sc] && g.W * 3 >= 2 * kTSeamHalf && (long long)n_frames * g.H >= 2 && !lab_int("X360_NO_SEAM", 0);
+    const bool seam_wanted = mc.wide_ok;
+    if (lab_int("X360_NO_WIDE_CLASSES", 0)) mc.wide_ok = false;
+    mc.seam_ok = seam_wanted && G.t_raw[sc] && g.W * 3 >= 2 * kTSeamHalf && (long long)n_frames * g.H >= 2 && !lab_int("X360_NO_SEAM", 0);
     memset(&mc.tms, 0, sizeof mc.tms);
     if ((mc.stage_ok || mc.store_ok) &&
         !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, mc.stage_ok != 0, out_views, n_frames * pl->p.n_views, g.oh, g.ow, t_th, mc.store_ok != 0,
-                           &mc.tms, pl->t_raw[sc], wide_rows, &mc.wide_ok, &mc.seam_ok)) {
+                           &mc.tms, G.t_raw[sc], wide_rows, &mc.wide_ok, &mc.seam_ok)) {
         mc.stage_ok = 0;                               // every tile goes direct, byte stores
         mc.store_ok = 0;
         mc.wide_ok = mc.seam_ok = false;
@@ -585,14 +614,11 @@ static const x360_plan::MapCache *tiled_maps(x360_plan *pl, x360_plan::MapCache 
 
 static int launch_score_pass(x360_plan *pl, const uint8_t *views, int n, int64_t *sum_lap, int64_t *sum_lap2, cudaStream_t st);
 
-static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint8_t *out_views, int64_t *sum_lap,
-                        int64_t *sum_lap2, cudaStream_t st)
+// One group's kernel launch(es) of an extract call.  `scratch`: this call's slot of the ring (already zeroed);
+// `gi`: group index (selects the work-item counters inside the slot).
+static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch, const uint8_t *frames, int n_frames, uint8_t *out_views,
+                        int64_t *sum_lap, int64_t *sum_lap2, cudaStream_t st)
 {
-    if (sum_lap && pl->split_score) {
-        // extraction without the fused score, then one streaming pass over the finished views
-        if (int rc = launch_tiled(pl, frames, n_frames, out_views, nullptr, nullptr, st)) return rc;
-        return launch_score_pass(pl, out_views, n_frames * pl->p.n_views, sum_lap, sum_lap2, st);
-    }
     const bool scores = sum_lap != nullptr;
     const Geom &g = pl->g;
     TiledArgs a;
@@ -604,43 +630,48 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     a.sum_lap2 = (long long *)sum_lap2;
     a.R = pl->d_R;
     a.lz_tab = pl->d_lz;
-    // this launch's slot of the scratch ring (work counter + tile-mode counters), zeroed on the launch stream
-    const int slot = pl->ring_next;
-    pl->ring_next = (slot + 1) % kRingSlots;
-    pl->ring_last = slot;
-    unsigned *scratch = pl->d_modes + (size_t)slot * kRingWords;
-    a.counter = scratch + 5;
+    a.counter = scratch + 5 + 2 * gi;
     a.tile_modes = scratch;
     a.F = n_frames;
     a.V = pl->p.n_views;
-    const int sc = scores ? 1 : 0, t_rows = pl->t_rows[sc], t_th = pl->t_th[sc];
+    const int sc = scores ? 1 : 0, t_rows = G.t_rows[sc], t_th = G.t_th[sc];
     a.rows_max = t_rows;
-    a.bw_max = pl->t_bw[sc];
+    a.bw_max = G.t_bw[sc];
     a.tiles_y = (g.oh + t_th - 1) / t_th;
-    a.col_u0 = pl->col_u0 ? 1 : 0;
+    a.col_u0 = G.col_u0 ? 1 : 0;
     a.aligned = ((uintptr_t)frames % 4 == 0) && (g.W % 4 == 0);
-    for (int c = 0; c < kTNumWide; ++c) a.wide_rows[c] = pl->wide_rows[sc][c];
+    for (int c = 0; c < kTNumWide; ++c) a.wide_rows[c] = G.wide_rows[sc][c];
 
-    // Work items = units x tiles x frame chunks, enough of them for the dynamic scheduler to balance the
-    // grid.  The map of a tile is evaluated once per item and the per-view setup once per (item, view), so
-    // prefer whole frame batches: split the view units first (8 -> 4 -> 2 -> 1 views), cut the batch into
-    // chunks only if that is still not enough.
-    const int cap = plan_grid(pl, scores);
+    // Work items = units x tiles x frame chunks.  The map of a tile is evaluated once per item and the per-view setup once per
+    // (item, view), so coarse units and whole batches amortise best — but the persistent grid needs several items per CTA to
+    // balance, and a small job (cfg1: 1024 tiles per view) cannot have both.  Pick the unit granularity (8 / 4 / 2 / 1 views)
+    // and the chunk count that minimise, in warp instructions per pixel and frame,
+    //     (walk + map / (views per unit x frames per chunk) + setup / frames per chunk) x (1 + k / items per CTA).
+    // Constants fitted to sweeps on a B200 (profiles/r02_chunking_sweep.txt): yaw-only groups walk 30, map 360, setup 30, k 1;
+    // general groups (pole faces: direct tiles, two record loads per pixel) walk 100, map 400, setup 60, k 2.4.
+    const int cap = G.grid_cap[sc];
     const long long tiles = (long long)g.tiles_x * a.tiles_y;
-    const long long want_items = 6LL * cap;
-    int level = 0;
-    while (level < 3 && pl->n_units[level] * tiles < want_items && pl->n_units[level + 1] > pl->n_units[level]) ++level;
-    if (pl->n_units[level] * tiles < want_items && n_frames > 1) level = 0;   // chunking needed anyway: keep the sharing
+    const double c_walk = G.col_u0 ? 30.0 : 100.0, c_map = G.col_u0 ? 360.0 : 400.0, c_setup = G.col_u0 ? 30.0 : 60.0, c_k = G.col_u0 ? 1.0 : 2.4;
+    int level = 0, n_chunks = 1;
+    double best_cost = 1e300;
+    for (int lv = 0; lv < 4; ++lv) {
+        if (lv > 0 && G.n_units[lv] == G.n_units[lv - 1]) continue;
+        const double vpu = (double)G.n_views / (double)G.n_units[lv];
+        for (int ch = 1; ch <= n_frames; ++ch) {
+            const int fg = (n_frames + ch - 1) / ch;
+            if (ch > 1 && (n_frames + ch - 2) / (ch - 1) == fg) continue;          // same chunk length as with one chunk fewer
+            const long long items = (long long)G.n_units[lv] * tiles * ((n_frames + fg - 1) / fg);
+            const double cost = (c_walk + c_map / (vpu * fg) + c_setup / fg) * (1.0 + c_k * (double)cap / (double)items);
+            if (cost < best_cost * 0.999) { best_cost = cost; level = lv; n_chunks = (n_frames + fg - 1) / fg; }
+        }
+    }
     if (const char *e = lab_env("X360_UNIT_LEVEL")) level = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : level;
-    const int n_units = pl->n_units[level];
-    a.units = pl->d_units[level];
-    a.unit_view = pl->d_unit_view[level];
-    a.unit_shift = pl->d_unit_shift[level];
+    const int n_units = G.n_units[level];
+    a.units = G.d_units[level];
+    a.unit_view = G.d_unit_view[level];
+    a.unit_shift = G.d_unit_shift[level];
     a.n_units = n_units;
-    long long want_chunks = (want_items + n_units * tiles - 1) / (n_units * tiles);
-    if (want_chunks < 1) want_chunks = 1;
-    if (want_chunks > n_frames) want_chunks = n_frames;
-    int FG = (int)((n_frames + want_chunks - 1) / want_chunks);
+    int FG = (n_frames + n_chunks - 1) / n_chunks;
     if (const char *e = lab_env("X360_FG")) FG = atoi(e) > 0 ? atoi(e) : FG;
     if (FG > n_frames) FG = n_frames;
     a.FG = FG;
@@ -649,18 +680,13 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     if (n_items > 0x7fffffff) return fail(X360_E_INVALID, "too many work items (%lld)", n_items);
     a.n_items = (int)n_items;
 
-    const bool two = pl->two_launch[sc] && pl->d_defer[0] != nullptr;
-    const x360_plan::MapCache *mc = tiled_maps(pl, pl->maps[sc], frames, n_frames, out_views, sc, t_rows, pl->wide_rows[sc]);
-    const x360_plan::MapCache *mc2 = two ? tiled_maps(pl, pl->maps2[sc], frames, n_frames, out_views, sc, pl->t2_rows[sc], pl->wide_rows2[sc]) : nullptr;
+    const bool two = G.two_launch[sc] && pl->d_defer[0] != nullptr;
+    const MapCache *mc = tiled_maps(pl, G, G.maps[sc], frames, n_frames, out_views, sc, t_rows, G.wide_rows[sc]);
+    const MapCache *mc2 = two ? tiled_maps(pl, G, G.maps2[sc], frames, n_frames, out_views, sc, G.t2_rows[sc], G.wide_rows2[sc]) : nullptr;
     a.stage_ok = mc->stage_ok;
     a.store_ok = mc->store_ok;
     a.wide_ok = mc->wide_ok ? 1 : 0;
     a.seam_ok = mc->seam_ok ? 1 : 0;
-    CU(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * kRingWords, st));
-    if (scores) {
-        CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
-        CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * a.V, st));
-    }
     int db = -1;
     if (two && mc->stage_ok && mc2->stage_ok) {
         // the deferred-pair list of this launch pair: one of kDeferBufs buffers; a buffer still in use by an earlier launch
@@ -670,32 +696,75 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
         if (pl->defer_used[db]) CU(cudaStreamWaitEvent(st, pl->defer_ev[db], 0));
         a.mode = 1;
         a.defer_cap = pl->defer_cap;
-        a.defer_sub = lab_int("X360_DEFER_SUB", n_frames >= 16 ? 4 : (n_frames >= 4 ? 2 : 1));
+        // frame sub-ranges per deferred pair: 1 (the map and per-view setup of a pair are paid once per item: cutting the 32-frame
+        // batch in 4 measured 8 % slower on cfg1 and cfg4)
+        a.defer_sub = lab_int("X360_DEFER_SUB", 1);
         a.defer_list = pl->d_defer[db];
         a.defer_count = pl->d_defer[db] + 2 * (size_t)pl->defer_cap;
         CU(cudaMemsetAsync(a.defer_count, 0, sizeof(unsigned), st));
     }
     const int grid = (int)std::min<long long>(n_items, cap);
-    const tiled_fn fn = pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, pl->col_u0, pl->t_raw[sc]);
-    fn<<<grid, 32 * tiled_warps(scores, t_th), pl->t_smem[sc], st>>>(a, mc->tms);
+    const tiled_fn fn = pick_tiled(scores, pl->p.interp == X360_INTERP_LANCZOS4, t_th, G.col_u0, G.t_raw[sc]);
+    fn<<<grid, 32 * tiled_warps(scores, t_th), G.t_smem[sc], st>>>(a, mc->tms);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     if (db >= 0) {
         a.mode = 2;
-        a.counter = scratch + 6;
-        a.rows_max = pl->t2_rows[sc];
-        a.bw_max = pl->t2_bw[sc];
-        for (int c = 0; c < kTNumWide; ++c) a.wide_rows[c] = pl->wide_rows2[sc][c];
+        a.counter = scratch + 6 + 2 * gi;
+        a.rows_max = G.t2_rows[sc];
+        a.bw_max = G.t2_bw[sc];
+        for (int c = 0; c < kTNumWide; ++c) a.wide_rows[c] = G.wide_rows2[sc][c];
         a.stage_ok = mc2->stage_ok;
         a.store_ok = mc2->store_ok;
         a.wide_ok = mc2->wide_ok ? 1 : 0;
         a.seam_ok = mc2->seam_ok ? 1 : 0;
-        fn<<<pl->grid_cap2[sc], 32 * tiled_warps(scores, t_th), pl->t2_smem[sc], st>>>(a, mc2->tms);
+        fn<<<G.grid_cap2[sc], 32 * tiled_warps(scores, t_th), G.t2_smem[sc], st>>>(a, mc2->tms);
         g_launches.fetch_add(1);
         CU(cudaGetLastError());
         CU(cudaEventRecord(pl->defer_ev[db], st));
         pl->defer_used[db] = true;
     }
+    return X360_OK;
+}
+
+static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint8_t *out_views, int64_t *sum_lap,
+                        int64_t *sum_lap2, cudaStream_t st)
+{
+    if (sum_lap && pl->split_score) {
+        // extraction without the fused score, then one streaming pass over the finished views
+        if (int rc = launch_tiled(pl, frames, n_frames, out_views, nullptr, nullptr, st)) return rc;
+        return launch_score_pass(pl, out_views, n_frames * pl->p.n_views, sum_lap, sum_lap2, st);
+    }
+    // this call's slot of the scratch ring (work counters + tile-mode counters), zeroed on the launch stream
+    const int slot = pl->ring_next;
+    pl->ring_next = (slot + 1) % kRingSlots;
+    pl->ring_last = slot;
+    unsigned *scratch = pl->d_modes + (size_t)slot * kRingWords;
+    CU(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * kRingWords, st));
+    if (sum_lap) {
+        CU(cudaMemsetAsync(sum_lap, 0, sizeof(int64_t) * (size_t)n_frames * pl->p.n_views, st));
+        CU(cudaMemsetAsync(sum_lap2, 0, sizeof(int64_t) * (size_t)n_frames * pl->p.n_views, st));
+    }
+    if (pl->n_groups < 2 || lab_int("X360_SERIAL_GROUPS", 0))  {
+        for (int gi = 0; gi < pl->n_groups; ++gi)
+            if (int rc = launch_group(pl, pl->grp[gi], gi, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, st)) return rc;
+        return X360_OK;
+    }
+    // Two groups: the second one (pole faces: the longer items) goes to a side stream forked from the caller's, so that each
+    // persistent grid fills the SMs the other one leaves idle at its tail; joined before returning to the caller's stream.
+    if (!pl->s_side) {
+        CU(cudaStreamCreateWithFlags(&pl->s_side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(pl->ev_fork, st));
+    CU(cudaStreamWaitEvent(pl->s_side, pl->ev_fork, 0));
+    int rc = launch_group(pl, pl->grp[1], 1, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, pl->s_side);
+    if (rc == X360_OK) rc = launch_group(pl, pl->grp[0], 0, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, st);
+    const std::string first_error = rc != X360_OK ? g_err : std::string();
+    const cudaError_t e1 = cudaEventRecord(pl->ev_join, pl->s_side), e2 = cudaStreamWaitEvent(st, pl->ev_join, 0);   // always re-join
+    if (rc != X360_OK) { g_err = first_error; return rc; }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(X360_E_CUDA, "joining the group streams failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     return X360_OK;
 }
 
@@ -754,13 +823,46 @@ int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit
             if (unit_of_view) unit_of_view[h.view[e]] = (int32_t)u;
             if (shift_px) shift_px[h.view[e]] = h.shift[e];
         }
+    // capacity / tile height of the group that serves view 0 (x360_plan_preview_views has them per view)
+    std::vector<double> Rg;
+    const bool col0 = column_only_map_x(params->R, 1);
+    for (int v = 0; v < params->n_views; ++v)
+        if (column_only_map_x(params->R + 9 * v, 1) == col0) Rg.insert(Rg.end(), params->R + 9 * v, params->R + 9 * v + 9);
     for (int sc = 0; sc < 2; ++sc) {
         int rows = 0, bw = 0, th = 0;
-        choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), params->R,
-                        params->n_views, params->interp == X360_INTERP_LANCZOS4, sc != 0, plan_opts(params->flags), &rows, &bw, &th);
+        choose_capacity(make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg), Rg.data(),
+                        (int)(Rg.size() / 9), params->interp == X360_INTERP_LANCZOS4, sc != 0, plan_opts(params->flags), &rows, &bw, &th);
         if (rows_max) rows_max[sc] = rows;
         if (bw_max) bw_max[sc] = bw;
         if (tile_h) tile_h[sc] = th;
+    }
+    return X360_OK;
+}
+
+int x360_plan_preview_views(const x360_params *params, int32_t *group_of_view, int32_t *tile_h_of_view)
+{
+    if (!params || !params->R || params->n_views < 1) return fail(X360_E_INVALID, "null argument");
+    if (params->struct_size != (int32_t)sizeof(x360_params)) return fail(X360_E_INVALID, "x360_params.struct_size mismatch");
+    if (int rc = check_dims(params->src_w, params->src_h, params->out_w, params->out_h)) return rc;
+    if (!(params->fov_deg > 0.0 && params->fov_deg < 180.0)) return fail(X360_E_INVALID, "fov_deg %g outside (0, 180)", params->fov_deg);
+    const Geom g = make_geom(params->src_w, params->src_h, params->out_w, params->out_h, params->fov_deg);
+    int next_group = 0;
+    for (int cls = 0; cls < 2; ++cls) {
+        std::vector<double> Rg;
+        std::vector<int> ids;
+        for (int v = 0; v < params->n_views; ++v)
+            if (column_only_map_x(params->R + 9 * v, 1) == (cls == 0)) { ids.push_back(v); Rg.insert(Rg.end(), params->R + 9 * v, params->R + 9 * v + 9); }
+        if (ids.empty()) continue;
+        int th[2] = {32, 32};
+        for (int sc = 0; sc < 2; ++sc) {
+            int rows = 0, bw = 0;
+            choose_capacity(g, Rg.data(), (int)ids.size(), params->interp == X360_INTERP_LANCZOS4, sc != 0, plan_opts(params->flags), &rows, &bw, &th[sc]);
+        }
+        for (int v : ids) {
+            if (group_of_view) group_of_view[v] = next_group;
+            if (tile_h_of_view) { tile_h_of_view[2 * v] = th[0]; tile_h_of_view[2 * v + 1] = th[1]; }
+        }
+        ++next_group;
     }
     return X360_OK;
 }
@@ -804,45 +906,66 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     pl->path = params->path == X360_PATH_DIRECT ? X360_PATH_DIRECT
                : (params->path == X360_PATH_STAGED ? X360_PATH_STAGED : X360_PATH_TILED);
     if (pl->path == X360_PATH_TILED) {
-        // staging capacity and tile height from a host survey of the tiles' footprints, without / with the score halo
         const bool lz = params->interp == X360_INTERP_LANCZOS4;
         pl->opts = plan_opts(params->flags);
-        pl->col_u0 = column_only_map_x(params->R, params->n_views) && !lab_int("X360_NO_COL_U0", 0);
         pl->split_score = score_is_split(pl->opts);
-        long long unfit[2] = {0, 0};
-        for (int sc = 0; sc < 2; ++sc) {
-            int rows = 40, bw = 144, th = 32;
-            choose_capacity(pl->g, params->R, params->n_views, lz, sc != 0, pl->opts, &rows, &bw, &th, &unfit[sc]);
-            const bool raw = tiled_raw(sc != 0, lz, pl->opts);
-            pl->t_raw[sc] = raw;
-            if (const char *e = lab_env("X360_TILED_BW")) {
-                const int v = atoi(e), unit = raw ? 64 : 48;
-                bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
-            }
-            if (const char *e = lab_env("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
-            while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw) > (size_t)kTiledSmemCap) rows -= kTBoxRows;
-            pl->t_th[sc] = th;
-            pl->t_bw[sc] = bw;
-            pl->t_rows[sc] = rows;
-            wide_class_rows(rows, bw, pl->wide_rows[sc]);
-            pl->t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, pl->col_u0, raw);
-            // the limit belongs to the kernel function, not to this plan: always the common cap (see kTiledSmemCap)
-            const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, pl->col_u0, raw), cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemCap);
-            if (ea != cudaSuccess) {
-                delete pl;
-                return fail(X360_E_CUDA, "cannot reserve %d B of shared memory: %s", kTiledSmemCap, cudaGetErrorString(ea));
-            }
-            pl->grid_cap[sc] = pl->sm_count * tiled_occupancy(pl, sc, pl->t_smem[sc]);
-            // a second launch with 16 KB staging buffers where the survey found footprints beyond this capacity (pole faces)
-            const int rows2 = lab_int("X360_T2_ROWS", 64), bw2 = lab_int("X360_T2_BW", raw ? 256 : 240);
-            if (!lz && !(raw && pl->col_u0) && !pl->opts.no_wide && unfit[sc] > 0 && rows2 * bw2 > rows * bw && !lab_int("X360_ONE_LAUNCH", 0)) {
-                pl->t2_rows[sc] = rows2;
-                pl->t2_bw[sc] = bw2;
-                wide_class_rows(rows2, bw2, pl->wide_rows2[sc]);
-                pl->t2_smem[sc] = tiled_smem_bytes(rows2, bw2, sc != 0, lz, th, pl->col_u0, raw);
-                if (pl->t2_smem[sc] <= (size_t)kTiledSmemCap) {
-                    pl->grid_cap2[sc] = pl->sm_count * tiled_occupancy(pl, sc, pl->t2_smem[sc]);
-                    pl->two_launch[sc] = true;
+        // groups: yaw-only views (column-only map_x) / the others
+        std::vector<int> members[2];
+        const bool no_col = lab_int("X360_NO_COL_U0", 0) != 0, one_group = lab_int("X360_ONE_GROUP", 0) != 0;
+        const bool all_col = column_only_map_x(params->R, params->n_views) && !no_col;
+        for (int v = 0; v < params->n_views; ++v) {
+            const bool col = one_group ? all_col : (column_only_map_x(params->R + 9 * v, 1) && !no_col);
+            members[col ? 0 : 1].push_back(v);
+        }
+        pl->view_group.assign((size_t)params->n_views, 0);
+        for (int cls = 0; cls < 2; ++cls) {
+            if (members[cls].empty()) continue;
+            TiledGroup &G = pl->grp[pl->n_groups];
+            for (int v : members[cls]) pl->view_group[(size_t)v] = pl->n_groups;
+            ++pl->n_groups;
+            G.n_views = (int)members[cls].size();
+            G.col_u0 = cls == 0;
+            std::vector<double> Rg((size_t)G.n_views * 9);
+            for (int i = 0; i < G.n_views; ++i) memcpy(&Rg[(size_t)i * 9], params->R + 9 * members[cls][(size_t)i], 9 * sizeof(double));
+            // staging capacity and tile height from a host survey of the group's tile footprints, without / with the score halo
+            for (int sc = 0; sc < 2; ++sc) {
+                int rows = 40, bw = 144, th = 32;
+                long long unfit = 0;
+                choose_capacity(pl->g, Rg.data(), G.n_views, lz, sc != 0, pl->opts, &rows, &bw, &th, &unfit);
+                const bool raw = tiled_raw(sc != 0, lz, pl->opts);
+                G.t_raw[sc] = raw;
+                if (const char *e = lab_env("X360_TILED_BW")) {
+                    const int v = atoi(e), unit = raw ? 64 : 48;
+                    bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
+                }
+                if (const char *e = lab_env("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
+                while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, G.col_u0, raw) > (size_t)kTiledSmemCap) rows -= kTBoxRows;
+                G.t_th[sc] = th;
+                G.t_bw[sc] = bw;
+                G.t_rows[sc] = rows;
+                wide_class_rows(rows, bw, G.wide_rows[sc]);
+                G.t_smem[sc] = tiled_smem_bytes(rows, bw, sc != 0, lz, th, G.col_u0, raw);
+                // the limit belongs to the kernel function, not to this plan: always the common cap (see kTiledSmemCap)
+                const cudaError_t ea = cudaFuncSetAttribute(pick_tiled(sc != 0, lz, th, G.col_u0, raw), cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemCap);
+                if (ea != cudaSuccess) {
+                    delete pl;
+                    return fail(X360_E_CUDA, "cannot reserve %d B of shared memory: %s", kTiledSmemCap, cudaGetErrorString(ea));
+                }
+                G.grid_cap[sc] = pl->sm_count * tiled_occupancy(pl, G, sc, G.t_smem[sc]);
+                // A second launch with 16 KB staging buffers for the footprints beyond this capacity (pole faces), where the
+                // survey finds enough of them to fill that launch's grid several times over: measured neutral on cfg4 (~5000
+                // pairs, direct share 12 % -> 2 %), 10 % slower on cfg1 (~1100 pairs: two half-empty waves), so small jobs keep
+                // the direct gathers for those tiles.
+                const int rows2 = lab_int("X360_T2_ROWS", 64), bw2 = lab_int("X360_T2_BW", raw ? 256 : 240);
+                if (!lz && !(raw && G.col_u0) && !pl->opts.no_wide && rows2 * bw2 > rows * bw && !lab_int("X360_ONE_LAUNCH", 0)) {
+                    G.t2_rows[sc] = rows2;
+                    G.t2_bw[sc] = bw2;
+                    wide_class_rows(rows2, bw2, G.wide_rows2[sc]);
+                    G.t2_smem[sc] = tiled_smem_bytes(rows2, bw2, sc != 0, lz, th, G.col_u0, raw);
+                    if (G.t2_smem[sc] <= (size_t)kTiledSmemCap) {
+                        G.grid_cap2[sc] = pl->sm_count * tiled_occupancy(pl, G, sc, G.t2_smem[sc]);
+                        G.two_launch[sc] = unfit >= (long long)lab_int("X360_DEFER_MIN_WAVES", 4) * G.grid_cap2[sc];
+                    }
                 }
             }
         }
@@ -873,7 +996,9 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     cudaError_t e = cudaMalloc(&pl->d_R, sizeof(double) * 9 * params->n_views);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_modes, sizeof(unsigned) * kRingSlots * kRingWords);
     if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * kRingSlots * kRingWords);
-    if (e == cudaSuccess && (pl->two_launch[0] || pl->two_launch[1])) {
+    bool any_two = false;
+    for (int gi = 0; gi < pl->n_groups; ++gi) any_two = any_two || pl->grp[gi].two_launch[0] || pl->grp[gi].two_launch[1];
+    if (e == cudaSuccess && any_two) {
         const long long pairs = (long long)params->n_views * pl->g.tiles_x * ((pl->g.oh + 15) / 16) * 8;      // (tile, view, frame chunk) triples, generously
         pl->defer_cap = (int)std::min<long long>(pairs, 1 << 18);
         for (int i = 0; i < x360_plan::kDeferBufs && e == cudaSuccess; ++i) {
@@ -883,15 +1008,24 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
     }
     if (e == cudaSuccess && pl->path == X360_PATH_TILED) {
         const bool share = !lab_int("X360_NO_SHARE", 0);
-        for (int lv = 0; lv < 4 && e == cudaSuccess; ++lv) {
-            const HostUnits h = build_units(params->R, params->n_views, params->src_w, pl->g, share, kTMaxUnitViews >> lv);
-            pl->n_units[lv] = (int)h.units.size();
-            e = cudaMalloc(&pl->d_units[lv], sizeof(TiledUnit) * h.units.size());
-            if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_view[lv], sizeof(int) * h.view.size());
-            if (e == cudaSuccess) e = cudaMalloc(&pl->d_unit_shift[lv], sizeof(double) * h.shift.size());
-            if (e == cudaSuccess) e = cudaMemcpy(pl->d_units[lv], h.units.data(), sizeof(TiledUnit) * h.units.size(), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_view[lv], h.view.data(), sizeof(int) * h.view.size(), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(pl->d_unit_shift[lv], h.shift.data(), sizeof(double) * h.shift.size(), cudaMemcpyHostToDevice);
+        for (int gi = 0; gi < pl->n_groups && e == cudaSuccess; ++gi) {
+            TiledGroup &G = pl->grp[gi];
+            std::vector<int> ids;
+            for (int v = 0; v < params->n_views; ++v)
+                if (pl->view_group[(size_t)v] == gi) ids.push_back(v);
+            std::vector<double> Rg(ids.size() * 9);
+            for (size_t i = 0; i < ids.size(); ++i) memcpy(&Rg[i * 9], params->R + 9 * ids[i], 9 * sizeof(double));
+            for (int lv = 0; lv < 4 && e == cudaSuccess; ++lv) {
+                HostUnits h = build_units(Rg.data(), (int)ids.size(), params->src_w, pl->g, share, kTMaxUnitViews >> lv);
+                for (int &v : h.view) v = ids[(size_t)v];                       // group-local -> plan view index
+                G.n_units[lv] = (int)h.units.size();
+                e = cudaMalloc(&G.d_units[lv], sizeof(TiledUnit) * h.units.size());
+                if (e == cudaSuccess) e = cudaMalloc(&G.d_unit_view[lv], sizeof(int) * h.view.size());
+                if (e == cudaSuccess) e = cudaMalloc(&G.d_unit_shift[lv], sizeof(double) * h.shift.size());
+                if (e == cudaSuccess) e = cudaMemcpy(G.d_units[lv], h.units.data(), sizeof(TiledUnit) * h.units.size(), cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) e = cudaMemcpy(G.d_unit_view[lv], h.view.data(), sizeof(int) * h.view.size(), cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) e = cudaMemcpy(G.d_unit_shift[lv], h.shift.data(), sizeof(double) * h.shift.size(), cudaMemcpyHostToDevice);
+            }
         }
     }
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_R, params->R, sizeof(double) * 9 * params->n_views, cudaMemcpyHostToDevice);
@@ -919,11 +1053,12 @@ int x360_plan_destroy(x360_plan *pl)
         cudaFree(pl->d_defer[i]);
         if (pl->defer_ev[i]) cudaEventDestroy(pl->defer_ev[i]);
     }
-    for (int lv = 0; lv < 4; ++lv) {
-        cudaFree(pl->d_units[lv]);
-        cudaFree(pl->d_unit_view[lv]);
-        cudaFree(pl->d_unit_shift[lv]);
-    }
+    for (int gi = 0; gi < 2; ++gi)
+        for (int lv = 0; lv < 4; ++lv) {
+            cudaFree(pl->grp[gi].d_units[lv]);
+            cudaFree(pl->grp[gi].d_unit_view[lv]);
+            cudaFree(pl->grp[gi].d_unit_shift[lv]);
+        }
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_frames[i]);
         cudaFree(pl->d_views[i]);
@@ -933,6 +1068,17 @@ int x360_plan_destroy(x360_plan *pl)
         if (pl->ev_k[i]) cudaEventDestroy(pl->ev_k[i]);
         if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
     }
+    if (pl->jpeg) x360_jpeg_destroy(pl->jpeg);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(pl->d_jpeg[i]);
+        cudaFree(pl->d_joff[i]);
+        if (pl->h_joff[i]) cudaFreeHost(pl->h_joff[i]);
+        if (pl->ev_off[i]) cudaEventDestroy(pl->ev_off[i]);
+    }
+    if (pl->s_off) cudaStreamDestroy(pl->s_off);
+    if (pl->s_side) cudaStreamDestroy(pl->s_side);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
     if (pl->s_k) cudaStreamDestroy(pl->s_k);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
@@ -960,8 +1106,8 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (!pl) return fail(X360_E_INVALID, "null plan");
     if (path) *path = pl->path;
     if (grid) *grid = plan_grid(pl, false);
-    if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->t_th[0]) : kThreads;
-    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->t_smem[0]
+    if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->grp[0].t_th[0]) : kThreads;
+    if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->grp[0].t_smem[0]
                                   : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
     return X360_OK;
 }
@@ -1339,6 +1485,272 @@ int x360_views_to_nchw(int32_t device, const uint8_t *views, int64_t n_views, in
         g_launches.fetch_add(1);
         CU(cudaGetLastError());
     }
+    return X360_OK;
+}
+
+// ---- baseline JPEG encode of view batches on the device (x360_jpeg.cuh) ---------------------------------------------
+struct x360_jpeg {
+    int device = 0, h = 0, w = 0, max_images = 0, quality = 95;
+    JpegGeom g;
+    JpegTables tab;
+    std::vector<uint8_t> header;
+    int max_segs = 0;
+    unsigned long long cap_words = 0;
+    // device scratch
+    int16_t *d_coef = nullptr;
+    uint32_t *d_bits = nullptr, *d_stream = nullptr, *d_segff = nullptr;
+    unsigned long long *d_view_bits = nullptr, *d_word_base = nullptr, *d_file_bytes = nullptr;
+    uint8_t *d_header = nullptr;
+    int *d_overflow = nullptr;
+    // host-path staging
+    uint8_t *d_images = nullptr, *d_out = nullptr;
+    long long *d_offsets = nullptr;
+};
+
+static int jpeg_launch(x360_jpeg *e, const uint8_t *images, int n, uint8_t *out, long long out_capacity, long long *offsets, cudaStream_t st)
+{
+    const JpegGeom &g = e->g;
+    CU(cudaMemsetAsync(e->d_overflow, 0, sizeof(int), st));
+    jpeg_blocks_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n), 128, 0, st>>>(images, g, e->tab, e->d_coef);
+    jpeg_dummy_dc_kernel<<<dim3((unsigned)((g.n_mcu + 127) / 128), (unsigned)n), 128, 0, st>>>(g, e->d_coef);
+    jpeg_bits_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n), 128, 0, st>>>(e->d_coef, g, e->d_bits);
+    jpeg_scan_kernel<<<(unsigned)n, 1024, 0, st>>>(e->d_bits, g.n_blocks, e->d_view_bits);
+    jpeg_bases_kernel<<<1, 32, 0, st>>>(e->d_view_bits, n, e->d_word_base, e->cap_words, e->d_overflow);
+    CU(cudaMemsetAsync(e->d_stream, 0, sizeof(uint32_t) * (size_t)e->cap_words, st));
+    jpeg_emit_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n), 128, 0, st>>>(e->d_coef, g, e->d_bits, e->d_word_base, e->d_stream, e->d_overflow);
+    jpeg_ffscan_kernel<<<(unsigned)n, 1024, 0, st>>>(e->d_stream, e->d_word_base, e->d_view_bits, e->d_segff, e->max_segs, (int)e->header.size(),
+                                                       e->d_file_bytes, e->d_overflow);
+    jpeg_offsets_kernel<<<1, 32, 0, st>>>(e->d_file_bytes, n, offsets, out_capacity, e->d_overflow);
+    jpeg_pack_kernel<<<dim3((unsigned)((e->max_segs + 1 + 127) / 128), (unsigned)n), 128, 0, st>>>(e->d_stream, e->d_word_base, e->d_view_bits, e->d_segff, e->max_segs,
+                                                                                                    e->d_header, (int)e->header.size(), offsets, out, e->d_overflow);
+    g_launches.fetch_add(9);
+    CU(cudaGetLastError());
+    return X360_OK;
+}
+
+int x360_jpeg_create(int32_t device, int32_t h, int32_t w, int32_t max_images, int32_t quality, x360_jpeg **out)
+{
+    if (!out) return fail(X360_E_INVALID, "null argument");
+    *out = nullptr;
+    if (h < 1 || w < 1 || h > 65535 || w > 65535) return fail(X360_E_INVALID, "bad image size %d x %d (JPEG dimensions are 16-bit)", h, w);
+    if (max_images < 1) return fail(X360_E_INVALID, "max_images must be positive");
+    if (quality < 1 || quality > 100) return fail(X360_E_INVALID, "quality %d outside [1, 100]", quality);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(X360_E_INVALID, "device %d out of range [0, %d)", device, n_dev);
+    CU(cudaSetDevice(device));
+    x360_jpeg *e = new (std::nothrow) x360_jpeg();
+    if (!e) return fail(X360_E_NOMEM, "out of host memory");
+    e->device = device; e->h = h; e->w = w; e->max_images = max_images; e->quality = quality;
+    JpegGeom &g = e->g;
+    g.h = h; g.w = w;
+    g.mw = (w + 15) / 16; g.mh = (h + 15) / 16;
+    g.bw_y = (w + 7) / 8; g.bh_y = (h + 7) / 8;
+    g.crows = (h + 1) / 2;
+    g.n_mcu = g.mw * g.mh; g.n_blocks = 6 * g.n_mcu;
+    jpeg_make_tables(quality, &e->tab);
+    e->header = jpeg_make_header(h, w, quality);
+    // Stream capacity: the raw size of the batch (3 bytes per pixel) + slack.  A quality-95 file of camera-like content is
+    // 5-15 % of that and of uniform noise 40 %; a batch that needs more is refused (X360_E_NOMEM), not truncated.
+    const size_t raw = (size_t)h * w * 3;
+    e->max_segs = (int)((raw + raw / 2 + 4096 + kJpegSeg - 1) / kJpegSeg);          // per view: 1.5 x its raw size
+    e->cap_words = ((unsigned long long)raw * (unsigned long long)max_images) / 4ull + 2ull * (unsigned long long)max_images + 1024ull;
+    JpegHuff hf;
+    jpeg_make_huff(&hf);
+    cudaError_t c = cudaMemcpyToSymbol(c_jpeg_huff, &hf, sizeof hf);
+    const size_t nb = (size_t)g.n_blocks * max_images;
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_coef, nb * 64 * sizeof(int16_t));
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_bits, nb * sizeof(uint32_t));
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_stream, (size_t)e->cap_words * sizeof(uint32_t));
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_segff, (size_t)e->max_segs * max_images * sizeof(uint32_t));
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_view_bits, sizeof(unsigned long long) * (size_t)max_images);
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_word_base, sizeof(unsigned long long) * ((size_t)max_images + 1));
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_file_bytes, sizeof(unsigned long long) * (size_t)max_images);
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_header, e->header.size());
+    if (c == cudaSuccess) c = cudaMalloc(&e->d_overflow, sizeof(int));
+    if (c == cudaSuccess) c = cudaMemcpy(e->d_header, e->header.data(), e->header.size(), cudaMemcpyHostToDevice);
+    if (c != cudaSuccess) {
+        x360_jpeg_destroy(e);
+        return fail(X360_E_CUDA, "jpeg encoder allocation failed: %s", cudaGetErrorString(c));
+    }
+    *out = e;
+    return X360_OK;
+}
+
+int x360_jpeg_destroy(x360_jpeg *e)
+{
+    if (!e) return X360_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_coef); cudaFree(e->d_bits); cudaFree(e->d_stream); cudaFree(e->d_segff); cudaFree(e->d_view_bits);
+    cudaFree(e->d_word_base); cudaFree(e->d_file_bytes); cudaFree(e->d_header); cudaFree(e->d_overflow);
+    cudaFree(e->d_images); cudaFree(e->d_out); cudaFree(e->d_offsets);
+    delete e;
+    return X360_OK;
+}
+
+int64_t x360_jpeg_max_bytes(const x360_jpeg *e, int32_t n_images)
+{
+    if (!e || n_images < 0) return 0;
+    return (int64_t)n_images * ((int64_t)e->h * e->w * 3 + (int64_t)e->header.size() + 64);
+}
+
+int x360_jpeg_encode_device(x360_jpeg *e, const uint8_t *images, int32_t n_images, uint8_t *out, int64_t out_capacity, int64_t *offsets,
+                            void *cuda_stream)
+{
+    if (!e || !images || !out || !offsets) return fail(X360_E_INVALID, "null argument");
+    if (n_images < 0 || n_images > e->max_images) return fail(X360_E_INVALID, "n_images %d outside [0, %d]", n_images, e->max_images);
+    if (out_capacity < 0) return fail(X360_E_INVALID, "negative capacity");
+    CU(cudaSetDevice(e->device));
+    if (n_images == 0) { CU(cudaMemsetAsync(offsets, 0, sizeof(int64_t), (cudaStream_t)cuda_stream)); return X360_OK; }
+    return jpeg_launch(e, images, n_images, out, (long long)out_capacity, (long long *)offsets, (cudaStream_t)cuda_stream);
+}
+
+int x360_jpeg_status(x360_jpeg *e, void *cuda_stream)
+{
+    if (!e) return fail(X360_E_INVALID, "null argument");
+    CU(cudaSetDevice(e->device));
+    int ov = 0;
+    CU(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    CU(cudaMemcpy(&ov, e->d_overflow, sizeof ov, cudaMemcpyDeviceToHost));
+    if (ov) return fail(X360_E_NOMEM, ov == 2 ? "jpeg output larger than the capacity given" : "jpeg stream larger than the encoder's scratch (3 bytes per pixel of the batch)");
+    return X360_OK;
+}
+
+int x360_jpeg_encode_host(x360_jpeg *e, const uint8_t *images, int64_t n_images, uint8_t *out, int64_t out_capacity, int64_t *offsets)
+{
+    if (!e || !images || !out || !offsets) return fail(X360_E_INVALID, "null argument");
+    if (n_images < 0 || out_capacity < 0) return fail(X360_E_INVALID, "negative count or capacity");
+    CU(cudaSetDevice(e->device));
+    const size_t img = (size_t)e->h * e->w * 3;
+    const long long dev_cap = (long long)x360_jpeg_max_bytes(e, e->max_images);
+    if (!e->d_images) CU(cudaMalloc(&e->d_images, img * e->max_images));
+    if (!e->d_out) CU(cudaMalloc(&e->d_out, (size_t)dev_cap));
+    if (!e->d_offsets) CU(cudaMalloc(&e->d_offsets, sizeof(long long) * ((size_t)e->max_images + 1)));
+    std::vector<long long> off((size_t)e->max_images + 1);
+    long long total = 0;
+    offsets[0] = 0;
+    for (int64_t n0 = 0; n0 < n_images; n0 += e->max_images) {
+        const int m = (int)std::min<int64_t>(e->max_images, n_images - n0);
+        CU(cudaMemcpy(e->d_images, images + (size_t)n0 * img, img * m, cudaMemcpyHostToDevice));
+        if (int rc = jpeg_launch(e, e->d_images, m, e->d_out, dev_cap, e->d_offsets, nullptr)) return rc;
+        if (int rc = x360_jpeg_status(e, nullptr)) return rc;
+        CU(cudaMemcpy(off.data(), e->d_offsets, sizeof(long long) * ((size_t)m + 1), cudaMemcpyDeviceToHost));
+        if (total + off[(size_t)m] > out_capacity)
+            return fail(X360_E_NOMEM, "jpeg output needs more than the %lld bytes given (at image %lld)", (long long)out_capacity, (long long)n0);
+        CU(cudaMemcpy(out + total, e->d_out, (size_t)off[(size_t)m], cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i) offsets[n0 + i + 1] = total + off[(size_t)i + 1];
+        total += off[(size_t)m];
+    }
+    return X360_OK;
+}
+
+int x360_jpeg_coefficients_host(x360_jpeg *e, const uint8_t *images, int32_t n_images, int16_t *coef)
+{
+    if (!e || !images || !coef) return fail(X360_E_INVALID, "null argument");
+    if (n_images < 0 || n_images > e->max_images) return fail(X360_E_INVALID, "n_images %d outside [0, %d]", n_images, e->max_images);
+    if (n_images == 0) return X360_OK;
+    CU(cudaSetDevice(e->device));
+    const size_t img = (size_t)e->h * e->w * 3;
+    if (!e->d_images) CU(cudaMalloc(&e->d_images, img * e->max_images));
+    CU(cudaMemcpy(e->d_images, images, img * n_images, cudaMemcpyHostToDevice));
+    const JpegGeom &g = e->g;
+    jpeg_blocks_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n_images), 128>>>(e->d_images, g, e->tab, e->d_coef);
+    jpeg_dummy_dc_kernel<<<dim3((unsigned)((g.n_mcu + 127) / 128), (unsigned)n_images), 128>>>(g, e->d_coef);
+    g_launches.fetch_add(2);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(coef, e->d_coef, (size_t)g.n_blocks * n_images * 64 * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return X360_OK;
+}
+
+int x360_jpeg_header(int32_t h, int32_t w, int32_t quality, uint8_t *out, int32_t capacity)
+{
+    if (h < 1 || w < 1 || h > 65535 || w > 65535 || quality < 1 || quality > 100) return fail(X360_E_INVALID, "bad jpeg header arguments");
+    const std::vector<uint8_t> hd = jpeg_make_header(h, w, quality);
+    if (out && capacity >= (int32_t)hd.size()) memcpy(out, hd.data(), hd.size());
+    return (int)hd.size();
+}
+
+// The pipelined host path with the save step's encode on the device: frames in (HOST), JPEG files out (HOST).
+int x360_extract_host_jpeg(x360_plan *pl, const uint8_t *frames, int32_t n_frames, int32_t quality, uint8_t *out, int64_t out_capacity,
+                           int64_t *offsets, int64_t *sum_lap, int64_t *sum_lap2)
+{
+    if (!pl || !frames || !out || !offsets) return fail(X360_E_INVALID, "null argument");
+    if (n_frames < 0 || out_capacity < 0) return fail(X360_E_INVALID, "negative frame count or capacity");
+    if ((sum_lap == nullptr) != (sum_lap2 == nullptr)) return fail(X360_E_INVALID, "sum_lap and sum_lap2 must both be given or both be NULL");
+    offsets[0] = 0;
+    if (n_frames == 0) return X360_OK;
+    CU(cudaSetDevice(pl->p.device));
+    if (int rc = pipe_setup(pl)) return rc;
+    const int V = pl->p.n_views, per = pl->chunk * V;
+    if (pl->jpeg && pl->jpeg->quality != quality) { x360_jpeg_destroy(pl->jpeg); pl->jpeg = nullptr; }
+    if (!pl->jpeg)
+        if (int rc = x360_jpeg_create(pl->p.device, pl->g.oh, pl->g.ow, per, quality, &pl->jpeg)) return rc;
+    pl->jpeg_cap = (long long)x360_jpeg_max_bytes(pl->jpeg, per);
+    if (!pl->s_off) CU(cudaStreamCreateWithFlags(&pl->s_off, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!pl->d_jpeg[i]) CU(cudaMalloc(&pl->d_jpeg[i], (size_t)pl->jpeg_cap));
+        if (!pl->d_joff[i]) CU(cudaMalloc(&pl->d_joff[i], sizeof(long long) * ((size_t)per + 2)));
+        if (!pl->h_joff[i]) CU(cudaHostAlloc(&pl->h_joff[i], sizeof(long long) * ((size_t)per + 2), cudaHostAllocDefault));
+        if (!pl->ev_off[i]) CU(cudaEventCreateWithFlags(&pl->ev_off[i], cudaEventDisableTiming));
+    }
+    const size_t fb = (size_t)pl->g.H * pl->g.W * 3;
+    const bool scores = sum_lap != nullptr;
+    long long base = 0;
+    int rc = X360_OK;
+    // finish chunk c: its offsets are on the host -> the size of its files is known -> download exactly those bytes
+    auto finish = [&](int c) -> int {
+        const int b = c & 1, f0 = c * pl->chunk, n = std::min(pl->chunk, n_frames - f0), m = n * V;
+        CU(cudaEventSynchronize(pl->ev_off[b]));
+        const long long *off = pl->h_joff[b];
+        if (off[m + 1] != 0) return fail(X360_E_NOMEM, "jpeg scratch too small for chunk %d (code %lld)", c, off[m + 1]);
+        if (base + off[m] > out_capacity) return fail(X360_E_NOMEM, "jpeg output needs more than the %lld bytes given (chunk %d)", (long long)out_capacity, c);
+        CU(cudaMemcpyAsync(out + base, pl->d_jpeg[b], (size_t)off[m], cudaMemcpyDeviceToHost, pl->s_out));
+        CU(cudaEventRecord(pl->ev_out[b], pl->s_out));
+        for (int i = 0; i < m; ++i) offsets[(size_t)f0 * V + i + 1] = base + off[i + 1];
+        base += off[m];
+        return X360_OK;
+    };
+    const int n_chunks = (n_frames + pl->chunk - 1) / pl->chunk;
+    for (int c = 0; c < n_chunks && rc == X360_OK; ++c) {
+        const int b = c & 1, f0 = c * pl->chunk, n = std::min(pl->chunk, n_frames - f0), m = n * V;
+        auto enqueue = [&]() -> int {
+            if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
+            CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+            CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
+            CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
+            if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));       // the files of chunk c-2 have left d_jpeg[b]
+            long long *ds = scores ? pl->d_sums[b] : nullptr;
+            long long *ds2 = scores ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
+            if (int r = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return r;
+            const uint8_t *d_result = pl->d_views[b];
+            if (pl->sharpen) {
+                if (int r = unsharp_launch(pl->d_views[b], (long long)m, pl->g.oh, pl->g.ow, pl->sharpen_strength, pl->d_sharp[b], pl->s_k)) return r;
+                d_result = pl->d_sharp[b];
+            }
+            if (int r = jpeg_launch(pl->jpeg, d_result, m, pl->d_jpeg[b], pl->jpeg_cap, pl->d_joff[b], pl->s_k)) return r;
+            CU(cudaMemsetAsync(pl->d_joff[b] + m + 1, 0, sizeof(long long), pl->s_k));
+            CU(cudaMemcpyAsync(pl->d_joff[b] + m + 1, pl->jpeg->d_overflow, sizeof(int), cudaMemcpyDeviceToDevice, pl->s_k));
+            CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
+            CU(cudaStreamWaitEvent(pl->s_off, pl->ev_k[b], 0));
+            CU(cudaMemcpyAsync(pl->h_joff[b], pl->d_joff[b], sizeof(long long) * ((size_t)m + 2), cudaMemcpyDeviceToHost, pl->s_off));
+            if (scores) {
+                CU(cudaMemcpyAsync(sum_lap + (size_t)f0 * V, ds, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
+                CU(cudaMemcpyAsync(sum_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
+            }
+            CU(cudaEventRecord(pl->ev_off[b], pl->s_off));
+            return X360_OK;
+        };
+        rc = enqueue();
+        if (rc == X360_OK && c >= 1) rc = finish(c - 1);
+    }
+    if (rc == X360_OK) rc = finish(n_chunks - 1);
+    const std::string first_error = rc != X360_OK ? g_err : std::string();
+    const cudaError_t e_out = cudaStreamSynchronize(pl->s_out), e_off = cudaStreamSynchronize(pl->s_off), e_k = cudaStreamSynchronize(pl->s_k),
+                      e_in = cudaStreamSynchronize(pl->s_in);
+    if (rc != X360_OK) { g_err = first_error; return rc; }
+    for (cudaError_t e : {e_out, e_off, e_k, e_in})
+        if (e != cudaSuccess) return fail(X360_E_CUDA, "pipelined extraction failed: %s", cudaGetErrorString(e));
     return X360_OK;
 }
 

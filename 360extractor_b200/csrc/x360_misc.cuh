@@ -209,34 +209,47 @@ blur_sums_march_kernel(const uint8_t *__restrict__ views, int h, int w, long lon
             const uint32_t *src = img + (size_t)y * pitch_w + col_w;
             r[0] = live ? __ldg(src) : 0u; r[1] = live ? __ldg(src + 1) : 0u; r[2] = live ? __ldg(src + 2) : 0u;
         };
-        uint32_t ra[3], rb[3], rc[3];
+        // rows are loaded four at a time, one group ahead of the group being summed: 2 x 4 x 12 bytes per lane in flight
+        uint32_t ra[3], rb[3], cur[4][3], nxt[4][3];
         load_row(r0 == 0 ? 1 : r0 - 1, ra);
         load_row(r0, rb);
-        load_row(min(r0 + 1, h - 1), rc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load_row(min(r0 + 1 + j, h - 1), cur[j]);
         uint32_t U = gray4_of(ra[0], ra[1], ra[2]), C = gray4_of(rb[0], rb[1], rb[2]);
         const bool counts = live && lane > 0 && lane < 31;                    // lanes 0 / 31: halo providers
         const bool at_left = x == 0, at_right = x + 3 == w - 1;
-#pragma unroll 2
-        for (int y = r0; y < r1; ++y) {
-            uint32_t D = (y + 1 < h) ? gray4_of(rc[0], rc[1], rc[2]) : U;     // reflect-101: g[h] = g[h-2]
-            if (y + 2 < r1 + 1 && y + 2 < h) load_row(y + 2, rc);             // two rows ahead of the one being summed
-            uint32_t l = __shfl_up_sync(0xffffffffu, C, 1) >> 24, r = __shfl_down_sync(0xffffffffu, C, 1) & 0xffu;
-            if (at_left) l = (C >> 8) & 0xffu;                                // g[-1] = g[1]
-            if (at_right) r = (C >> 16) & 0xffu;                              // g[w] = g[w-2]
-            const uint32_t Lw = __byte_perm(C, l, 0x2104);                    // [l, c0, c1, c2]
-            const uint32_t Rw = __byte_perm(C, r, 0x4321);                    // [c1, c2, c3, r]
-            constexpr uint32_t kA = 0x0001fc01u;                              // [ 1, -4,  1,  0]
-            constexpr uint32_t kB = 0x01fc0100u;                              // [ 0,  1, -4,  1]
-            const int L0 = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
-            const int L1 = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
-            const int L2 = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
-            const int L3 = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
-            if (counts) {
-                pl += L0 + L1 + L2 + L3;
-                pl2 += (unsigned)(L0 * L0) + (unsigned)(L1 * L1) + (unsigned)(L2 * L2) + (unsigned)(L3 * L3);
+#pragma unroll 1
+        for (int y0 = r0; y0 < r1; y0 += 4) {
+            if (y0 + 4 < r1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_row(min(y0 + 5 + j, h - 1), nxt[j]);
             }
-            U = C;
-            C = D;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int y = y0 + j;
+                if (y < r1) {                                                 // uniform over the warp
+                    const uint32_t D = (y + 1 < h) ? gray4_of(cur[j][0], cur[j][1], cur[j][2]) : U;     // reflect-101: g[h] = g[h-2]
+                    uint32_t l = __shfl_up_sync(0xffffffffu, C, 1) >> 24, r = __shfl_down_sync(0xffffffffu, C, 1) & 0xffu;
+                    if (at_left) l = (C >> 8) & 0xffu;                        // g[-1] = g[1]
+                    if (at_right) r = (C >> 16) & 0xffu;                      // g[w] = g[w-2]
+                    const uint32_t Lw = __byte_perm(C, l, 0x2104);            // [l, c0, c1, c2]
+                    const uint32_t Rw = __byte_perm(C, r, 0x4321);            // [c1, c2, c3, r]
+                    constexpr uint32_t kA = 0x0001fc01u;                      // [ 1, -4,  1,  0]
+                    constexpr uint32_t kB = 0x01fc0100u;                      // [ 0,  1, -4,  1]
+                    const int L0 = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
+                    const int L1 = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
+                    const int L2 = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
+                    const int L3 = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
+                    if (counts) {
+                        pl += L0 + L1 + L2 + L3;
+                        pl2 += (unsigned)(L0 * L0) + (unsigned)(L1 * L1) + (unsigned)(L2 * L2) + (unsigned)(L3 * L3);
+                    }
+                    U = C;
+                    C = D;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { cur[j][0] = nxt[j][0]; cur[j][1] = nxt[j][1]; cur[j][2] = nxt[j][2]; }
         }
     }
     pl = __reduce_add_sync(0xffffffffu, pl);

@@ -50,9 +50,14 @@ def plan_preview(src_h, src_w, out_res, fov_deg, R, interpolation_mode="linear",
     shift = np.zeros(p.n_views, np.float64)
     check(lib().x360_plan_preview(ctypes.byref(p), ctypes.byref(n_units), unit.ctypes.data, shift.ctypes.data,
                                   rows, bw, th))
+    group = np.zeros(p.n_views, np.int32)
+    th_view = np.zeros((p.n_views, 2), np.int32)
+    check(lib().x360_plan_preview_views(ctypes.byref(p), group.ctypes.data, th_view.ctypes.data))
     return {"n_units": n_units.value, "unit_of_view": unit.tolist(), "shift_px": shift.tolist(),
             "rows_max": rows[0], "bw_max": bw[0], "tile_h": th[0],
-            "with_scores": {"rows_max": rows[1], "bw_max": bw[1], "tile_h": th[1]}}
+            "with_scores": {"rows_max": rows[1], "bw_max": bw[1], "tile_h": th[1]},
+            # groups: yaw-only views / the others, each with its own kernel variant and tile height
+            "group_of_view": group.tolist(), "tile_h_of_view": th_view[:, 0].tolist(), "tile_h_of_view_fused_score": th_view[:, 1].tolist()}
 
 
 def column_only_map_x(R) -> bool:
@@ -145,8 +150,7 @@ class Extractor:
                 "staged_wide": int(out[3]), "staged_seam": int(out[4])}
 
     # -- the hot path --------------------------------------------------------------------------
-    def _host_batch(self, frames, out):
-        """Validate a host frame batch and its output buffer (the C side trusts the sizes it is given)."""
+    def _host_frames(self, frames):
         frames = np.asarray(frames)
         if frames.dtype != np.uint8:
             raise TypeError(f"frames must be uint8 (got {frames.dtype}); the reference's frames are always 8-bit BGR")
@@ -155,7 +159,11 @@ class Extractor:
             frames = frames[None]
         if frames.ndim != 4 or frames.shape[1:] != self.frame_shape:
             raise ValueError(f"frames shape {frames.shape} does not match plan {self.frame_shape}")
-        F = frames.shape[0]
+        return frames, frames.shape[0]
+
+    def _host_batch(self, frames, out):
+        """Validate a host frame batch and its output buffer (the C side trusts the sizes it is given)."""
+        frames, F = self._host_frames(frames)
         if out is None:
             out = np.empty(self.views_shape(F), np.uint8)
         elif not isinstance(out, np.ndarray) or out.shape != self.views_shape(F) or out.dtype != np.uint8 or not out.flags.c_contiguous \
@@ -184,6 +192,38 @@ class Extractor:
         s2 = np.zeros((F, self.n_views), np.int64)
         check(lib().x360_extract_host(self._plan, ptr(frames), F, ptr(out), ptr(s), ptr(s2)))
         return out, s, s2
+
+    def jpeg_capacity(self, n_frames):
+        """Bytes that always hold the files of ``n_frames`` frames (the raw size of the views plus headers)."""
+        return n_frames * self.n_views * (self.out_h * self.out_w * 3 + 1024)
+
+    def extract_jpeg_into(self, frames, out, offsets, quality=95, sum_lap=None, sum_lap2=None):
+        """Low-level form of ``extract_jpeg``: the files go back to back into ``out`` (uint8, 1-D, pinned for full speed) and
+        their byte offsets into ``offsets`` (int64 ``[F * V + 1]``); returns the total number of bytes."""
+        frames, F = self._host_frames(frames)
+        n = F * self.n_views
+        if out.dtype != np.uint8 or out.ndim != 1 or not out.flags.c_contiguous or offsets.dtype != np.int64 or offsets.size < n + 1:
+            raise ValueError("out must be a 1-D uint8 array and offsets an int64 array of at least F * V + 1 entries")
+        check(lib().x360_extract_host_jpeg(self._plan, ptr(frames), F, int(quality), ptr(out), int(out.size), ptr(offsets), ptr(sum_lap), ptr(sum_lap2)))
+        return int(offsets[n])
+
+    def extract_jpeg(self, frames, quality=95, want_scores=False):
+        """Like ``extract`` but the views come back as the ``.jpg`` files the reference's save step would write
+        (``cv2.imwrite(path, view, [cv2.IMWRITE_JPEG_QUALITY, quality])``, src/core/processor.py:121-123,
+        src/utils/file_manager.py:21-32) — encoded on the device, so only compressed bytes cross PCIe.
+
+        Returns ``(files, scores)``: ``files[f][v]`` is a ``bytes`` object, byte-identical to cv2's encode of the same view."""
+        frames, F = self._host_frames(frames)
+        n = F * self.n_views
+        out = np.empty(self.jpeg_capacity(F), np.uint8)
+        off = np.zeros(n + 1, np.int64)
+        s = s2 = None
+        if want_scores:
+            s = np.zeros((F, self.n_views), np.int64)
+            s2 = np.zeros((F, self.n_views), np.int64)
+        self.extract_jpeg_into(frames, out, off, quality, s, s2)
+        files = [[out[off[f * self.n_views + v]:off[f * self.n_views + v + 1]].tobytes() for v in range(self.n_views)] for f in range(F)]
+        return files, (scores_from_sums(s, s2, self.pixels_per_view) if want_scores else None)
 
     def extract_device(self, frames, out, sum_lap=None, sum_lap2=None, stream=None):
         """Device-resident batch (torch CUDA tensors or raw device addresses); asynchronous on ``stream``.

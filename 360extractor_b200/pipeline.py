@@ -99,6 +99,23 @@ class ExtractionSession:
                     kept.append(ViewResult(f, name, views[f, v], score))
         return kept
 
+    def process_encoded(self, frames, quality=None):
+        """``process`` with the save step's encode on the device: the kept views come back as the ``.jpg`` files
+        ``FileManager.save_image`` would write (src/core/processor.py:121-123,428-431; quality = settings 'quality', default 95),
+        byte-identical to cv2's, and only compressed bytes cross PCIe.  Returns ``[(frame_index, camera, jpeg_bytes, score)]``."""
+        if quality is None:
+            quality = self.settings.get("quality", 95)
+        if self.extractor is None:
+            return []
+        files, scores = self.extractor.extract_jpeg(frames, quality=quality, want_scores=self.blur.enabled)
+        kept = []
+        for f in range(len(files)):
+            for v, name in enumerate(self.names):
+                score = float(scores[f, v]) if scores is not None else None
+                if self.blur.accept(score):
+                    kept.append((f, name, files[f][v], score))
+        return kept
+
     def process_sharded(self, frames, rank: int, world_size: int, group=None):
         """Frame-sharded variant: this rank reprojects frames ``shard_bounds(F, world, rank)``, the
         score sums are all-gathered and every rank replays the blur machine over the full table.

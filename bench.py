@@ -54,6 +54,10 @@ WORKLOADS = {
                  desc="7680x3840 clip -> cube 6x1920^2 bilinear (diagnostic: cfg4 without the blur score)"),
     "cfg4_ring": dict(W=7680, H=3840, layout="ring", n=6, pitch=0, active=None, d=1920, fov=90, mode="linear", scores=True, F=32,
                  desc="7680x3840 clip -> ring 6x1920^2 bilinear + blur score (diagnostic: cfg4 without the pole faces)"),
+    "cfg1_h4": dict(W=3840, H=1920, layout="cube", n=6, pitch=0, active=[0, 1, 2, 3], d=1024, fov=90, mode="linear", scores=False, F=32,
+                 desc="diagnostic: cfg1's four horizontal faces only"),
+    "cfg1_polar": dict(W=3840, H=1920, layout="cube", n=6, pitch=0, active=[4, 5], d=1024, fov=90, mode="linear", scores=False, F=32,
+                 desc="diagnostic: cfg1's Up / Down faces only"),
     "cfg5": dict(W=11520, H=5760, layout="ring", n=12, pitch=0, active=[0, 3, 6, 9], d=2048, fov=90, mode="lanczos", scores=False, F=1,
                  desc="11520x5760 -> ring 12 (active 0,3,6,9) 2048^2 Lanczos4"),
 }
@@ -228,7 +232,20 @@ def cpu_baseline_block(wl, V, with_one_thread=True):
             cv2.setNumThreads(1)
             one = V * d * d / cpu_reference_step(cv2_path, wl, cviews, maps, cframes[:1]) / 1e6
             cv2.setNumThreads(os.cpu_count() or 1)
+        enc = None
+        try:                                            # the save step beside it: cv2.imencode of every view (what cv2.imwrite computes)
+            t0 = time.perf_counter()
+            cnt = 0
+            for nm in list(maps)[:2]:
+                mx, my = maps[nm]
+                v = cv2.remap(cframes[0], mx, my, cv2.INTER_LANCZOS4 if wl["mode"] == "lanczos" else cv2.INTER_LINEAR, borderMode=cv2.BORDER_WRAP)
+                cv2.imencode(".jpg", v, [cv2.IMWRITE_JPEG_QUALITY, 95])
+                cnt += 1
+            enc = cnt * d * d / (time.perf_counter() - t0) / 1e6
+        except Exception:
+            pass
         return {"value": n * V * d * d / best / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                "remap_plus_jpeg_one_thread_value": enc, "remap_plus_jpeg_sample": "2 views: cv2.remap + cv2.imencode(q95), as the reference's loop + one saver thread do",
                 "sample": f"{n} frame(s) x {V} views, best of 3, maps pre-built once ({map_s:.2f} s, untimed as in processor.py:259-265)",
                 "one_thread_value": one, "one_thread_sample": "1 frame, 1 pass, cv2.setNumThreads(1)",
                 "host_cpus": os.cpu_count(), "cpu_model": cpu_model(), "cv2": cv2.__version__, "numpy": np.__version__, "map_build_s": map_s}
@@ -288,7 +305,7 @@ def int_roofline(mpix, sm_mhz):
             "model": "96 dp2a per output pixel; IDP.2A at 1 warp instruction / 2 cycles / SM sub-partition, 148 SMs at %.0f MHz" % (clk / 1e6)}
 
 
-def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, world, steps, warmup, with_e2e, with_cpu, sampler=None):
+def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, world, steps, warmup, with_e2e, with_cpu, sampler=None, with_jpeg=False):
     """Kernel-only value + roofline (+ e2e, + CPU baseline) of one workload on this rank's GPU; returns a dict."""
     F, H, W, d = wl["F"], wl["H"], wl["W"], wl["d"]
     views = pkg.GeometryProcessor.generate_views(wl["n"], pitch_offset=wl["pitch"], layout_mode=wl["layout"])
@@ -391,7 +408,31 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
                       "h2d_bytes_per_step": F * H * W * 3, "d2h_bytes_per_step": F * V * d * d * 3 + (16 * F * V if wl["scores"] else 0),
                       "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                       "api": "Extractor.extract(pinned numpy) -> x360_extract_host (chunked H2D / kernel / D2H on side streams)"}
-        pin_in.free(); pin_out.free()
+        pin_out.free()
+        if with_jpeg:
+            # the same call with the reference's save step on the device: frames in, the .jpg files (quality 95, byte-identical
+            # to cv2.imwrite's) out — only compressed bytes cross PCIe on the way back
+            jcap = min(ex.jpeg_capacity(F), 2 * F * H * W * 3 + (64 << 20))
+            pin_j = pkg.PinnedBuffer((jcap,))
+            off = np.zeros(F * V + 1, np.int64)
+            total = ex.extract_jpeg_into(pin_in.array, pin_j.array, off, 95)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                total = ex.extract_jpeg_into(pin_in.array, pin_j.array, off, 95)
+            torch.cuda.synchronize()
+            j_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([j_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                j_s = float(t.item())
+            res["e2e_encoded"] = {"value": out_pix_per_step * e2e_steps / j_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * 3,
+                                  "d2h_bytes_per_step": int(total), "jpeg_quality": 95, "bytes_per_output_pixel": total / (F * V * d * d),
+                                  "steps": e2e_steps, "ms_per_step": 1e3 * j_s / e2e_steps,
+                                  "api": "Extractor.extract_jpeg_into(pinned numpy) -> x360_extract_host_jpeg (H2D / extract / JPEG encode / D2H of the files)",
+                                  "parity": "files byte-identical to cv2.imencode('.jpg', view, [IMWRITE_JPEG_QUALITY, 95]) (tests/test_gpu_parity.py)"}
+            pin_j.free()
+        pin_in.free()
     else:
         res["e2e"] = None
     res["cpu_baseline"] = cpu_baseline_block(wl, V) if with_cpu else None
@@ -528,7 +569,8 @@ def main():
     sampler.start()                       # nvidia-smi needs ~100 ms to start: begin before the warm-up
     full = not args.kernel_only
     main_res = bench_workload(pkg, torch, dist, args, args.workload, wl, dev, local_rank, rank, world, args.steps, args.warmup,
-                              with_e2e=full and not args.no_e2e, with_cpu=full and not args.no_cpu_baseline and rank == 0 and world == 1, sampler=sampler)
+                              with_e2e=full and not args.no_e2e, with_cpu=full and not args.no_cpu_baseline and rank == 0 and world == 1, sampler=sampler,
+                              with_jpeg=full and not args.no_e2e and wl["mode"] != "none")
 
     extra = {}
     if full and not args.no_extra and args.workload == "cfg2" and args.frames == 0:
@@ -554,6 +596,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": main_res["config"], "views_per_s": main_res["views_per_s"],
             "roofline": main_res["roofline"], "cpu_baseline": main_res["cpu_baseline"], "e2e": main_res["e2e"],
+            "e2e_encoded": main_res.get("e2e_encoded"),
             "gpu_launches": main_res["gpu_launches"], "clocks": main_res.get("clocks"), "plan": main_res["plan"], "lib": pkg.version(),
         }
         if "roofline_int" in main_res:

@@ -74,8 +74,8 @@ typedef struct x360_params {
 /* x360_params.flags: explicit overrides of what the plan would choose by itself (every variant computes the same bytes;
  * the parity suite runs each one).  The library reads no environment variable unless it is built with -DX360_LAB. */
 #define X360_FLAG_PLANES       1   /* bilinear: pair-record planes (transform pass) instead of the raw gather */
-#define X360_FLAG_FUSED_SCORE  2   /* blur score fused into the extraction kernel (tile + 1-px halo) */
-#define X360_FLAG_SPLIT_SCORE  4   /* blur score by one streaming pass over the finished views */
+#define X360_FLAG_FUSED_SCORE  2   /* blur score fused into the extraction kernel (gray tile + 1-px halo per output tile) */
+#define X360_FLAG_SPLIT_SCORE  4   /* blur score by one streaming pass over the finished views (the default: measured faster) */
 #define X360_FLAG_TILE_H16     8   /* 32 x 16 output tiles */
 #define X360_FLAG_TILE_H32    16   /* 32 x 32 output tiles */
 #define X360_FLAG_NO_WIDE     32   /* no wide / seam boxes: tiles beyond the regular staging capacity take the direct gathers */
@@ -157,6 +157,13 @@ double x360_focal(int32_t out_w, double fov_deg);
  */
 int x360_plan_preview(const x360_params *params, int32_t *n_units, int32_t *unit_of_view, double *shift_px,
                       int32_t *rows_max, int32_t *bw_max, int32_t *tile_h);
+/*
+ * A plan serves its views in one or two groups, each with its own kernel variant, tile height and launch: the yaw-only
+ * views (map_x independent of the output row: rings at pitch 0, the four horizontal cube faces) and the others (pole
+ * faces, inclined and fibonacci views).  group_of_view [n_views]; tile_h_of_view [n_views][2] (without / with a fused
+ * score).  x360_plan_preview's rows_max / bw_max / tile_h describe the group of view 0.  Host-only.
+ */
+int x360_plan_preview_views(const x360_params *params, int32_t *group_of_view, int32_t *tile_h_of_view);
 
 /*
  * Device-resident hand-off of a view batch to the masker: replaces the host round trip of
@@ -197,6 +204,48 @@ int x360_unsharp_host(int32_t device, const uint8_t *images, int64_t n_images, i
  * (geometry.py:30-33).  Such plans keep one fp64 map_x row per warp instead of a tile and run 7 CTAs per SM.
  */
 int x360_column_only_map_x(const double *R, int32_t n_views);
+
+/*
+ * Baseline JPEG encode of a view batch on the device (the codec step after the path): replaces the
+ * reference's save step
+ *     cv2.imwrite(path, rect_img, [cv2.IMWRITE_JPEG_QUALITY, quality])     src/utils/file_manager.py:21-32,
+ *     save_params at src/core/processor.py:121-123, quality default 95 (src/core/settings_manager.py:24)
+ * so that only compressed bytes cross PCIe.  Parity definition: the bytes of every file are IDENTICAL to what cv2.imwrite /
+ * cv2.imencode of opencv-python 4.13.0 (libjpeg-turbo 3.1.2) produce for the same pixels and quality: YCbCr 4:2:0, baseline
+ * sequential, integer "islow" DCT, IJG-scaled Annex-K quantisation tables, Annex-K Huffman tables, JFIF 1.01 header.
+ * images: uint8 [n][h][w][3] BGR.  The files are written back to back into `out`; offsets [n + 1] (int64) receives the
+ * byte offset of each file and, last, the total.
+ *   x360_jpeg_create          encoder for images of h x w, at most max_images per call, quality 1..100
+ *   x360_jpeg_encode_device   DEVICE pointers (images, out, offsets), asynchronous on cuda_stream; x360_jpeg_status
+ *                             synchronises the stream and reports X360_E_NOMEM if out_capacity (or the encoder's scratch,
+ *                             3 bytes per pixel of the batch) was too small — nothing is written past the capacity
+ *   x360_jpeg_encode_host     HOST pointers, any n (chunks of max_images), synchronous
+ *   x360_jpeg_max_bytes       a capacity that always suffices for n_images
+ *   x360_jpeg_coefficients_host  the quantised DCT coefficients: int16 [n][mcus][6][64], per 16 x 16 MCU the blocks
+ *                             Y00 Y01 Y10 Y11 Cb Cr in zigzag order (inspection / tests)
+ *   x360_jpeg_header          host-only: the SOI..SOS header of an h x w file; returns its length
+ */
+typedef struct x360_jpeg x360_jpeg;
+int x360_jpeg_create(int32_t device, int32_t h, int32_t w, int32_t max_images, int32_t quality, x360_jpeg **out_encoder);
+int x360_jpeg_destroy(x360_jpeg *encoder);
+int64_t x360_jpeg_max_bytes(const x360_jpeg *encoder, int32_t n_images);
+int x360_jpeg_encode_device(x360_jpeg *encoder, const uint8_t *images, int32_t n_images, uint8_t *out, int64_t out_capacity,
+                            int64_t *offsets, void *cuda_stream);
+int x360_jpeg_status(x360_jpeg *encoder, void *cuda_stream);
+int x360_jpeg_encode_host(x360_jpeg *encoder, const uint8_t *images, int64_t n_images, uint8_t *out, int64_t out_capacity,
+                          int64_t *offsets);
+int x360_jpeg_coefficients_host(x360_jpeg *encoder, const uint8_t *images, int32_t n_images, int16_t *coef);
+int x360_jpeg_header(int32_t h, int32_t w, int32_t quality, uint8_t *out, int32_t capacity);
+
+/*
+ * x360_extract_host with the save step's encode on the device: frames in (HOST), one JPEG file per (frame, view) out (HOST).
+ * Replaces src/core/processor.py:327-390 + the cv2.imwrite of :428-431 for a frame batch: extraction (+ blur sums, + the
+ * unsharp mask if x360_plan_set_sharpen is on) -> x360_jpeg encode of the chunk's views -> download of the files only.
+ * out: the files back to back in (frame, view) order; offsets: int64 [n_frames * n_views + 1].  Files of views the caller's
+ * blur filter rejects are simply not written to disk by the caller (the sums come back as in x360_extract_host).
+ */
+int x360_extract_host_jpeg(x360_plan *plan, const uint8_t *frames, int32_t n_frames, int32_t quality, uint8_t *out,
+                           int64_t out_capacity, int64_t *offsets, int64_t *sum_lap, int64_t *sum_lap2);
 
 /* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
 int x360_host_alloc(size_t bytes, void **out_ptr);

@@ -20,8 +20,8 @@ INTERP_LANCZOS4 = 1
 
 def build(force: bool = False) -> str:
     """Compile the C oracle with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "x360_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("x360_oracle.c", "x360_jpeg_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libx360_oracle.so"])
     return _SO
 
@@ -164,3 +164,61 @@ def add_weighted(a, g, strength):
     out = np.empty_like(a)
     lib().orc_add_weighted(_p(a, ctypes.c_uint8), _p(g, ctypes.c_uint8), a.size, float(strength), _p(out, ctypes.c_uint8))
     return out
+
+
+# ---- baseline JPEG (x360_jpeg_oracle.c): what cv2.imwrite(..., [IMWRITE_JPEG_QUALITY, q]) writes -----------------------
+def _jpeg_lib():
+    L = lib()
+    if not getattr(L, "_jpeg_ready", False):
+        u8p, i16p, u16p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int16), ctypes.POINTER(ctypes.c_uint16)
+        L.orc_jpeg_encode.restype = ctypes.c_size_t
+        L.orc_jpeg_encode.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_size_t]
+        L.orc_jpeg_header.restype = ctypes.c_size_t
+        L.orc_jpeg_header.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_size_t]
+        L.orc_jpeg_coefficients.restype = ctypes.c_long
+        L.orc_jpeg_coefficients.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i16p]
+        L.orc_jpeg_qtables.restype = None
+        L.orc_jpeg_qtables.argtypes = [ctypes.c_int, u8p, u8p]
+        L.orc_jpeg_huffman.restype = None
+        L.orc_jpeg_huffman.argtypes = [u16p, u8p]
+        L._jpeg_ready = True
+    return L
+
+
+def jpeg_encode(img, quality=95) -> bytes:
+    """uint8 BGR [h][w][3] -> the bytes of the .jpg file the reference's save step writes."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    cap = 1024 + 2 * h * w * 3 + 4096
+    buf = np.empty(cap, np.uint8)
+    n = _jpeg_lib().orc_jpeg_encode(_p(img, ctypes.c_uint8), h, w, int(quality), _p(buf, ctypes.c_uint8), cap)
+    assert 0 < n <= cap
+    return buf[:n].tobytes()
+
+
+def jpeg_header(h, w, quality=95) -> bytes:
+    buf = np.empty(1024, np.uint8)
+    n = _jpeg_lib().orc_jpeg_header(int(h), int(w), int(quality), _p(buf, ctypes.c_uint8), 1024)
+    return buf[:n].tobytes()
+
+
+def jpeg_coefficients(img, quality=95):
+    """int16 [mcus][6][64]: quantised coefficients per 16 x 16 MCU (Y00 Y01 Y10 Y11 Cb Cr), zigzag order."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    n = ((h + 15) // 16) * ((w + 15) // 16)
+    out = np.empty((n, 6, 64), np.int16)
+    _jpeg_lib().orc_jpeg_coefficients(_p(img, ctypes.c_uint8), h, w, int(quality), _p(out, ctypes.c_int16))
+    return out
+
+
+def jpeg_qtables(quality=95):
+    a, b = np.empty(64, np.uint8), np.empty(64, np.uint8)
+    _jpeg_lib().orc_jpeg_qtables(int(quality), _p(a, ctypes.c_uint8), _p(b, ctypes.c_uint8))
+    return a, b
+
+
+def jpeg_huffman():
+    code, size = np.empty((4, 256), np.uint16), np.empty((4, 256), np.uint8)
+    _jpeg_lib().orc_jpeg_huffman(_p(code, ctypes.c_uint16), _p(size, ctypes.c_uint8))
+    return code, size

@@ -168,7 +168,41 @@ def unsharp_fixture():
     return arrays, {"cases": meta, "add_weighted_table_sha": table, "line_response": [int(v) for v in col]}
 
 
+def jpeg_image(kind, h, w, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if kind == "smooth":
+        lo = rng.integers(0, 256, (max(1, h // 8) + 1, max(1, w // 8) + 1, 3), dtype=np.uint8)
+        return np.ascontiguousarray(cv2.resize(lo, (w, h), interpolation=cv2.INTER_CUBIC))
+    if kind == "flat":
+        return np.full((h, w, 3), int(rng.integers(0, 256)), np.uint8)
+    return (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)          # saturated
+
+
+JPEG_CASES = [(kind, h, w, q) for q in (95, 75, 100, 30) for kind in ("noise", "smooth", "flat", "sat")
+              for (h, w) in ((16, 16), (48, 64), (17, 33), (100, 100), (8, 8), (233, 77), (24, 40), (1, 1), (256, 256))]
+
+
+def jpeg_fixture():
+    """What the reference's save step writes: cv2.imencode('.jpg', img, [IMWRITE_JPEG_QUALITY, q]) == the bytes cv2.imwrite
+    puts in the file (src/utils/file_manager.py:21-32, src/core/processor.py:121-123)."""
+    out = []
+    for i, (kind, h, w, q) in enumerate(JPEG_CASES):
+        img = jpeg_image(kind, h, w, 1000 + i)
+        ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])
+        assert ok
+        out.append({"kind": kind, "h": h, "w": w, "quality": q, "seed": 1000 + i, "image_sha": sha(img), "bytes": int(buf.size),
+                    "jpeg_sha": hashlib.sha256(buf.tobytes()).hexdigest()})
+    return {"cases": out, "cv2": cv2.__version__, "libjpeg": "libjpeg-turbo (bundled with the opencv-python wheel)"}
+
+
 def main():
+    if "--only-jpeg" in sys.argv:
+        with open(os.path.join(HERE, "jpeg_cases.json"), "w") as f:
+            json.dump(jpeg_fixture(), f, indent=1)
+        print("jpeg fixtures written")
+        return
     if "--only-unsharp" in sys.argv:
         arrays, meta = unsharp_fixture()
         np.savez_compressed(os.path.join(HERE, "unsharp_cases.npz"), **arrays)
@@ -190,6 +224,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "unsharp_cases.npz"), **arrays)
     with open(os.path.join(HERE, "unsharp.json"), "w") as f:
         json.dump(meta, f, indent=1)
+    with open(os.path.join(HERE, "jpeg_cases.json"), "w") as f:
+        json.dump(jpeg_fixture(), f, indent=1)
     info = {"cv2": cv2.__version__, "numpy": np.__version__, "reference": REF,
             "threads": cv2.getNumThreads()}
     with open(os.path.join(HERE, "PROVENANCE.json"), "w") as f:

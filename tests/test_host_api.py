@@ -341,3 +341,12 @@ def test_blur_machine_reproduces_the_reference_worker(x360, name):
     assert want == kept
     if "smart" in name or "legacy" in name:
         assert filt.forced >= 1 and filt.skipped >= 1
+
+
+def test_jpeg_header_matches_the_oracle(x360):
+    """Host-only piece of the device JPEG encoder: the SOI..SOS header (quantisation tables for the quality, SOF0 4:2:0,
+    Annex-K Huffman tables) equals the oracle's, which is pinned to cv2's files."""
+    from oracle import c_oracle
+    for (h, w, q) in [(1600, 1600, 95), (48, 64, 75), (1, 1, 100), (2048, 2048, 1), (100, 333, 50)]:
+        assert x360.jpeg_header(h, w, q) == c_oracle.jpeg_header(h, w, q), (h, w, q)
+    assert len(x360.jpeg_header(16, 16)) == 623

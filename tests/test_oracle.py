@@ -140,3 +140,47 @@ def test_oracle_unsharp_bit_exact_on_golden(oracle):
         # blur alone: addWeighted(img, 0, blur, 1) == blur  <=>  strength -1
         assert np.array_equal(oracle.unsharp(img, -1.0), z[f"blur{k}"]), m["name"]
         assert np.array_equal(oracle.unsharp(img, s), z[f"out{k}"]), m["name"]
+
+
+# ---- baseline JPEG: the reference's save step (cv2.imwrite with IMWRITE_JPEG_QUALITY) ---------------------------------
+def _jpeg_image(kind, h, w, seed):
+    """Same generator as tests/golden/make_golden.py::jpeg_image (the fixture carries the image hash)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if kind == "smooth":
+        lo = rng.integers(0, 256, (max(1, h // 8) + 1, max(1, w // 8) + 1, 3), dtype=np.uint8)
+        return np.ascontiguousarray(cv2.resize(lo, (w, h), interpolation=cv2.INTER_CUBIC))
+    if kind == "flat":
+        return np.full((h, w, 3), int(rng.integers(0, 256)), np.uint8)
+    return (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+
+
+def test_jpeg_oracle_matches_cv2_fixture(oracle):
+    """orc_jpeg_encode == the bytes cv2 wrote when the fixture was made (sha256 per file), for every committed case:
+    all qualities, sizes that are not multiples of 16 (dummy blocks, edge expansion), flat and saturated images."""
+    import hashlib
+    fx = load_json("jpeg_cases.json")
+    assert len(fx["cases"]) >= 100
+    for c in fx["cases"]:
+        img = _jpeg_image(c["kind"], c["h"], c["w"], c["seed"])
+        h = hashlib.sha256()
+        h.update(np.ascontiguousarray(img).tobytes())
+        if h.hexdigest() != c["image_sha"]:
+            pytest.skip("this cv2 build resizes differently from the one that made the fixture: image hashes differ")
+        got = oracle.jpeg_encode(img, c["quality"])
+        assert len(got) == c["bytes"] and hashlib.sha256(got).hexdigest() == c["jpeg_sha"], c
+
+
+def test_jpeg_oracle_matches_live_cv2(oracle):
+    """The same against the cv2 of the box the test runs on (the wheel is part of the image)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(99)
+    for (h, w, q) in [(32, 32, 95), (50, 70, 95), (64, 48, 60), (31, 17, 90), (128, 256, 95), (40, 24, 100), (400, 400, 95)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        img[: h // 2] = (img[: h // 2].astype(np.uint16) // 4 + 100).astype(np.uint8)            # a calmer half
+        ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])
+        assert ok and oracle.jpeg_encode(img, q) == buf.tobytes(), (h, w, q)
+        # and it decodes to the same pixels as cv2's own file
+        assert np.array_equal(cv2.imdecode(np.frombuffer(oracle.jpeg_encode(img, q), np.uint8), cv2.IMREAD_COLOR), cv2.imdecode(buf, cv2.IMREAD_COLOR))
