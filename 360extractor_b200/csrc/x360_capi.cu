@@ -462,8 +462,12 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
                 // cost per tile: 1 in a regular box, 3 otherwise.  Wide boxes and the second launch take most of the rest off the
                 // direct path, but measured (cfg1, cfg4) they do not pay for a larger capacity: a cube plan runs 11 % faster
                 // with 32-row buffers than with 40-row ones at the same 7 CTAs/SM, so the capacity is chosen for the regular tiles.
+                // A group of general views (pole faces) is another matter: it is latency-bound whatever the capacity (measured:
+                // the same 0.36 ms for cfg1's pole faces from 27 KB to 58 KB of shared memory), and a wide box is far cheaper
+                // than gathering the tile from global memory, so there the tiles a wide class takes count as covered too.
                 const double n = (double)(total ? total : 1);
-                const double cost = ((double)fit + 3.0 * (double)(total - fit)) / n;
+                const double covered = (double)fit + (col ? 0.0 : (double)fit_wide);
+                const double cost = (covered + 3.0 * ((double)total - covered)) / n;
                 const double score = th_factor * occ_factor[occ] / cost;
                 if (score > best * 1.0001) { best = score; best_rows = r; best_bw = bw; best_th = th; best_unfit = (long long)(total - fit - fit_wide); }
             }
@@ -934,11 +938,12 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
                 choose_capacity(pl->g, Rg.data(), G.n_views, lz, sc != 0, pl->opts, &rows, &bw, &th, &unfit);
                 const bool raw = tiled_raw(sc != 0, lz, pl->opts);
                 G.t_raw[sc] = raw;
-                if (const char *e = lab_env("X360_TILED_BW")) {
+                const bool lab_cap = !(lab_int("X360_TILED_GENERAL_ONLY", 0) && G.col_u0);
+                if (const char *e = lab_cap ? lab_env("X360_TILED_BW") : nullptr) {
                     const int v = atoi(e), unit = raw ? 64 : 48;
                     bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
                 }
-                if (const char *e = lab_env("X360_TILED_ROWS")) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
+                if (const char *e = lab_cap ? lab_env("X360_TILED_ROWS") : nullptr) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
                 while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, G.col_u0, raw) > (size_t)kTiledSmemCap) rows -= kTBoxRows;
                 G.t_th[sc] = th;
                 G.t_bw[sc] = bw;

@@ -90,30 +90,40 @@ __device__ __forceinline__ double fast_atan2(double y, double x)
 }
 
 // geometry.py:149-190 for one output pixel -> fp64 map_x (unrounded) and the float32 map_y.
-// Every rounding of the reference's sequence is kept (no contraction); the only freedom against
-// numpy is the last ulps of atan2 / asin (asin(v1 / |v|) is evaluated as atan2(v1, hypot(v0, v2))),
-// which the float32 cast + Q5 rounding absorbs except with probability ~1e-10 per pixel
-// ("map exactness").
-__device__ __forceinline__ void map_ray(const double *__restrict__ R, const Geom &g, int x, int y, double &v0, double &v1, double &v2)
+// The ray v = [xn, yn, 1] @ R.T keeps every rounding of the reference's sequence (no contraction): where a pixel looks straight at a
+// pole its components are rounding residues and decide the result.  From the ray on, the only freedom against numpy is the last ulp
+// or two of the angles: atan2 / asin (asin(v1 / |v|) is evaluated as atan2(v1, hypot(v0, v2))) and the divisions by 2 pi and pi,
+// which are multiplications by the rounded reciprocals here (a division costs ~13 fp64 instructions) — all absorbed by the float32
+// cast + Q5 rounding except with probability ~1e-10 per pixel ("map exactness").
+__device__ __forceinline__ double map_xn(const Geom &g, int x) { return __ddiv_rn((double)x - g.cx, g.f); }
+__device__ __forceinline__ double map_yn(const Geom &g, int y) { return __ddiv_rn((double)y - g.cy, g.f); }
+__device__ __forceinline__ void map_ray_n(const double *__restrict__ R, double xn, double yn, double &v0, double &v1, double &v2)
 {
-    const double xn = __ddiv_rn((double)x - g.cx, g.f);
-    const double yn = __ddiv_rn((double)y - g.cy, g.f);
     // [xn, yn, 1] @ R.T  (geometry.py:164)
     v0 = __dadd_rn(__fma_rn(yn, R[1], __dmul_rn(xn, R[0])), R[2]);
     v1 = __dadd_rn(__fma_rn(yn, R[4], __dmul_rn(xn, R[3])), R[5]);
     v2 = __dadd_rn(__fma_rn(yn, R[7], __dmul_rn(xn, R[6])), R[8]);
 }
+__device__ __forceinline__ void map_ray(const double *__restrict__ R, const Geom &g, int x, int y, double &v0, double &v1, double &v2)
+{
+    map_ray_n(R, map_xn(g, x), map_yn(g, y), v0, v1, v2);
+}
+constexpr double kInvTwoPi = 0.15915494309189535;       // fl(1 / 2 pi)
+constexpr double kInvPi = 0.3183098861837907;           // fl(1 / pi)
 // fp64 map_x before the float32 cast (geometry.py:172,183)
 __device__ __forceinline__ double map_u_of(const Geom &g, double v0, double v2)
 {
-    return __dmul_rn(__dadd_rn(__ddiv_rn(fast_atan2(v0, v2), kTwoPi), 0.5), (double)g.W);
+    return __dmul_rn(__dadd_rn(__dmul_rn(fast_atan2(v0, v2), kInvTwoPi), 0.5), (double)g.W);
 }
-// float32 map_y (geometry.py:175-176,186,190)
-__device__ __forceinline__ float map_y_of(const Geom &g, double v0, double v1, double v2)
+// |(v0, v2)|: the horizontal length of the ray (geometry.py:175)
+__device__ __forceinline__ double map_rxz(double v0, double v2) { return sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v2, v2))); }
+// float32 map_y (geometry.py:175-176,186,190) from v1 and the horizontal length
+__device__ __forceinline__ float map_y_from(const Geom &g, double v1, double rxz)
 {
-    const double phi = fast_atan2(v1, sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v2, v2))));
-    return __double2float_rn(__dmul_rn(__dadd_rn(__ddiv_rn(phi, kPi), 0.5), (double)g.H));
+    const double phi = fast_atan2(v1, rxz);
+    return __double2float_rn(__dmul_rn(__dadd_rn(__dmul_rn(phi, kInvPi), 0.5), (double)g.H));
 }
+__device__ __forceinline__ float map_y_of(const Geom &g, double v0, double v1, double v2) { return map_y_from(g, v1, map_rxz(v0, v2)); }
 __device__ __forceinline__ void map_f64(const double *__restrict__ R, const Geom &g, int x, int y, double &uf, float &my)
 {
     double v0, v1, v2;

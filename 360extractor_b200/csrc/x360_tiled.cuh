@@ -65,6 +65,13 @@ constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
 #define X360_RAW_NB 3
 #endif
 constexpr int kTRawBufs = X360_RAW_NB;   // raw buffers of the raw-gather variant (the TMA box of frame f + NB - 1 flies during frame f)
+// ... of the column-only plans.  The general variant (pole faces, inclined views) is latency-bound at 5 CTAs per SM (ncu: issue
+// slots 44 % busy, long + short scoreboard stalls): it takes two larger buffers instead of three — fewer tiles on the direct
+// gathers at the same shared memory per CTA.
+#ifndef X360_RAW_NB_GENERAL
+#define X360_RAW_NB_GENERAL 2
+#endif
+__host__ __device__ constexpr int tiled_raw_bufs(bool col_only) { return col_only ? kTRawBufs : X360_RAW_NB_GENERAL; }
 
 // Wide boxes: tiles whose footprint is wider than the regular capacity but still fits the raw buffer as a flatter box
 // (near the poles a 32-px tile spans 32 / r rad of longitude at r px from the pole; the footprint is a few rows of
@@ -184,7 +191,7 @@ __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, boo
 {
     // RAW: ctrl | packed tile | map_y | [gray] | map_x | raw x3 | second packed tile | [second gray tile | second per-warp sums]
     // (+ with the fused score: second gray tile, second set of per-warp sums — a frame's barrier is shared by both copies)
-    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + kTRawBufs * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3 +
+    if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + tiled_raw_bufs(col_only) * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3 +
                     (scores ? tiled_gray_bytes(th) + 128u : 0u);
     // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
     return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
@@ -503,7 +510,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     static_assert(TP == 8 || TP == 4, "the gather is written out for 8 or 4 rows per thread");
     static_assert(NW == 4 || (NW == 2 && !SCORES), "the halo of the fused score needs 64 + 2 TH threads");
     constexpr int kTP = TP;
-    constexpr int NB = RAW ? kTRawBufs : 2;                                         // raw buffers
+    constexpr int NB = RAW ? tiled_raw_bufs(COLSEL) : 2;                            // raw buffers
     constexpr int kTW = NW, kTT = 32 * NW;                                          // warps / threads per CTA
     constexpr int TH = kTW * TP;                                                    // tile height
     TiledCtrl &ctl = *reinterpret_cast<TiledCtrl *>(dsm + kOffCtl);
@@ -588,15 +595,23 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
         {
             const double *R = a.R + 9 * a.unit_view[unit.first];
             const int x = min(x0 + lane, g.ow - 1);
+            const double xn = map_xn(g, x);
+            // yn of this warp's rows: lane k divides for row k, the loop broadcasts (a division per pixel otherwise)
+            const double yn_lane = map_yn(g, min(y0 + warp * kTP + min(lane, kTP - 1), g.oh - 1));
+            double rxz = 0.0;
             int sy_hi = 0;
-#pragma unroll 1
+            // (Lanczos4 plans are typically single-frame jobs — nothing amortises the map — and run 12 warps per SM: two pixels
+            // per iteration give the dependent fp64 chains of atan2 some instruction-level parallelism)
+            constexpr int kMapUnroll = LZ ? 2 : 1;
+#pragma unroll kMapUnroll
             for (int k = 0; k < kTP; ++k) {
                 double v0, v1, v2;
-                map_ray(R, g, x, min(y0 + warp * kTP + k, g.oh - 1), v0, v1, v2);
-                // yaw-only rotations: v0 and v2, hence map_x, do not depend on the row: one atan2 per column and warp
-                if (!col_u0) u0s[k * kTT + tid] = map_u_of(g, v0, v2);
-                else if (k == 0) u0s[lane] = map_u_of(g, v0, v2);
-                const int syq = q5_of(map_y_of(g, v0, v1, v2));            // 0 .. 32 H < 2^20
+                map_ray_n(R, xn, __shfl_sync(0xffffffffu, yn_lane, k), v0, v1, v2);
+                // yaw-only rotations: v0 and v2 — hence map_x and the ray's horizontal length — do not depend on the row:
+                // one atan2 and one square root per column and warp
+                if (!col_u0) { u0s[k * kTT + tid] = map_u_of(g, v0, v2); rxz = map_rxz(v0, v2); }
+                else if (k == 0) { u0s[lane] = map_u_of(g, v0, v2); rxz = map_rxz(v0, v2); }
+                const int syq = q5_of(map_y_from(g, v1, rxz));             // 0 .. 32 H < 2^20
                 sy_s[k * kTT + tid] = (uint8_t)syq;
                 sy_s[TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 8);
                 if (k & 1) sy_s[2 * TH * kTile + (k >> 1) * kTT + tid] = (uint8_t)(sy_hi | ((syq >> 16) << 4));   // bits 16-19 of rows k-1, k

@@ -1,8 +1,8 @@
 """Summarise an ncu report (--set full) for profiles/: the metrics DESIGN.md and bench.py cite.
 
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01x_ncu_summary.csv "note" [traffic_key]
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01x_ncu_summary.csv "note" [traffic_key] [launch_index]
 
-Writes one CSV (metric, unit, value) for the first kernel in the report, the per-region shared-memory
+Writes one CSV (metric, unit, value) for one kernel launch of the report (the first by default), the per-region shared-memory
 wavefront breakdown and the top stall sites from the source page, and — when traffic_key is given —
 records dram bytes per launch in profiles/traffic.json for bench.py's roofline.traffic."""
 import csv
@@ -32,16 +32,28 @@ def page(rep, name):
 
 def main():
     rep, dst, note = sys.argv[1], sys.argv[2], sys.argv[3]
-    key = sys.argv[4] if len(sys.argv) > 4 else None
+    key = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None
+    idx = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     raw = page(rep, "raw")
-    hdr, units, vals = raw[0], raw[1], raw[2]
+    hdr, units, vals = raw[0], raw[1], raw[2 + idx]
     rows = [("# " + note, "", ""), ("kernel", "", vals[hdr.index("Kernel Name")])]
     got = {}
     for i, h in enumerate(hdr):
         if h in KEEP or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")):
             rows.append((h, units[i], vals[i]))
             got[h] = (units[i], vals[i])
-    src = page(rep, "source")
+    try:
+        src = page(rep, "source") if idx == 0 else [[], []]
+        if len(src) >= 3:
+            ix0 = {h: i for i, h in enumerate(src[1])}
+            _ = [int(r[ix0["# Samples"]]) for r in src[2:]]          # multi-kernel reports print ragged source pages: skip them
+    except Exception:
+        src = [[], []]
+    if len(src) < 3:
+        with open(dst, "w", newline="") as f:
+            csv.writer(f).writerows(rows)
+        print("wrote", dst, "(no source page for this launch index)")
+        return
     sh, data = src[1], src[2:]
     ix = {h: i for i, h in enumerate(sh)}
     tot_s = sum(int(r[ix["# Samples"]]) for r in data) or 1
