@@ -56,6 +56,7 @@ SYMBOLS = {
     "x360_unsharp_host": (ctypes.c_int, [_i32, _vp, _i64, _i32, _i32, _dbl, _vp]),
     "x360_views_to_nchw": (ctypes.c_int, [_i32, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "x360_lanczos4_table": (ctypes.c_int, [_vp]),
+    "x360_lanczos4_factors": (ctypes.c_int, [_vp, _vp]),
     "x360_focal": (_dbl, [_i32, _dbl]),
     "x360_plan_preview": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(_i32), _vp, _vp, _vp, _vp, _vp]),
     "x360_plan_preview_views": (ctypes.c_int, [ctypes.POINTER(Params), _vp, _vp]),

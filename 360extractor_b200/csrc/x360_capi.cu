@@ -521,6 +521,8 @@ struct x360_plan {
     int sm_count = 0;
     double *d_R = nullptr;
     int16_t *d_lz = nullptr;
+    float *d_lz_k1 = nullptr;            // Lanczos4: the table's factors (x360_tables.hpp lanczos4_factors)
+    uint32_t *d_lz_fix = nullptr;
     int path = X360_PATH_DIRECT;        // resolved path of the extraction kernel
     int px_max = 0, rows_max = 0, pp = 0, raw_pitch = 0;
     size_t smem = 0;                     // dynamic shared memory of the staged kernel
@@ -634,6 +636,8 @@ static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch,
     a.sum_lap2 = (long long *)sum_lap2;
     a.R = pl->d_R;
     a.lz_tab = pl->d_lz;
+    a.lz_k1 = pl->d_lz_k1;
+    a.lz_fix = pl->d_lz_fix;
     a.counter = scratch + 5 + 2 * gi;
     a.tile_modes = scratch;
     a.F = n_frames;
@@ -806,6 +810,17 @@ int x360_lanczos4_table(int16_t *out)
     if (!out) return fail(X360_E_INVALID, "null table pointer");
     const std::vector<int16_t> t = lanczos4_q15_table();
     memcpy(out, t.data(), t.size() * sizeof(int16_t));
+    return X360_OK;
+}
+
+int x360_lanczos4_factors(float *k1d, uint32_t *fix)
+{
+    if (!k1d || !fix) return fail(X360_E_INVALID, "null pointer");
+    std::vector<float> k;
+    std::vector<uint32_t> f;
+    lanczos4_factors(k, f);
+    memcpy(k1d, k.data(), k.size() * sizeof(float));
+    memcpy(fix, f.data(), f.size() * sizeof(uint32_t));
     return X360_OK;
 }
 
@@ -1038,6 +1053,13 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         const std::vector<int16_t> t = lanczos4_q15_table();
         e = cudaMalloc(&pl->d_lz, t.size() * sizeof(int16_t));
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_lz, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice);
+        std::vector<float> k1d;
+        std::vector<uint32_t> fix;
+        lanczos4_factors(k1d, fix);
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_lz_k1, k1d.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_lz_fix, fix.size() * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_lz_k1, k1d.data(), k1d.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_lz_fix, fix.data(), fix.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) {
         x360_plan_destroy(pl);
@@ -1053,6 +1075,8 @@ int x360_plan_destroy(x360_plan *pl)
     cudaSetDevice(pl->p.device);
     cudaFree(pl->d_R);
     cudaFree(pl->d_lz);
+    cudaFree(pl->d_lz_k1);
+    cudaFree(pl->d_lz_fix);
     cudaFree(pl->d_modes);
     for (int i = 0; i < x360_plan::kDeferBufs; ++i) {
         cudaFree(pl->d_defer[i]);

@@ -68,4 +68,26 @@ inline std::vector<int16_t> lanczos4_q15_table()
     return tab;
 }
 
+// The same table as its factors: the 32 x 8 float32 1-D coefficients and, per (fy, fx), the one tap the sum-to-2^15 fix-up
+// changed — position p in bits 0-1 (tap (4 + (p >> 1), 4 + (p & 1))), residue in bits 16-31 (signed).  The kernel computes the
+// 64 weights from these (x360_tiled.cuh, lanczos_pairs); tests rebuild the table from them and compare.
+inline void lanczos4_factors(std::vector<float> &k1d, std::vector<uint32_t> &fix)
+{
+    k1d.assign(32 * 8, 0.f);
+    for (int q = 0; q < 32; ++q) lanczos4_kernel_1d((float)q * (1.f / 32), &k1d[(size_t)q * 8]);
+    const std::vector<int16_t> tab = lanczos4_q15_table();
+    fix.assign(1024, 0u);
+    for (int fy = 0; fy < 32; ++fy)
+        for (int fx = 0; fx < 32; ++fx) {
+            const int16_t *e = &tab[(size_t)(fy * 32 + fx) * 64];
+            for (int pos = 0; pos < 4; ++pos) {
+                const int r = 4 + (pos >> 1), c = 4 + (pos & 1);
+                long q = std::lrintf(k1d[(size_t)fy * 8 + r] * k1d[(size_t)fx * 8 + c] * 32768.f);
+                q = q < -32768 ? -32768 : (q > 32767 ? 32767 : q);
+                const int delta = (int)e[r * 8 + c] - (int)q;
+                if (delta != 0) fix[(size_t)(fy * 32 + fx)] = (uint32_t)pos | ((uint32_t)(uint16_t)(int16_t)delta << 16);
+            }
+        }
+}
+
 }  // namespace x360

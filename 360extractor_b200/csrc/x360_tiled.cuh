@@ -107,7 +107,9 @@ struct TiledArgs {
     uint8_t *out;                     // [F][V][oh][ow][3]
     long long *sum_lap, *sum_lap2;    // [F][V] or nullptr
     const double *R;                  // [V][9]
-    const int16_t *lz_tab;            // [1024][8][8] Lanczos4 weights (Lanczos4 plans only)
+    const int16_t *lz_tab;            // [1024][8][8] Lanczos4 weights (Lanczos4 plans only; the direct gathers read it)
+    const float *lz_k1;               // [32][8] cv2's 1-D Lanczos-4 coefficients (float32)
+    const uint32_t *lz_fix;           // [1024] per (fy, fx): the table's sum-to-2^15 fix-up — tap (4 + (p >> 1), 4 + (p & 1)), p = bits 0-1; delta = bits 16-31 (signed)
     const TiledUnit *units;           // [n_units], largest units first
     const int *unit_view;             // view index per table entry
     const double *unit_shift;         // map_x shift (source pixels, in [0, W)) per table entry
@@ -193,9 +195,8 @@ __host__ __device__ inline size_t tiled_smem_bytes(int rows_max, int bw_max, boo
     // (+ with the fused score: second gray tile, second set of per-warp sums — a frame's barrier is shared by both copies)
     if (raw) return (size_t)tiled_off_raw(scores, th, col_only) + tiled_raw_bufs(col_only) * tiled_raw_bytes(rows_max, bw_max) + (size_t)th * kTile * 3 +
                     (scores ? tiled_gray_bytes(th) + 128u : 0u);
-    // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records | [Lanczos4: per-warp weight staging, 32 x 144 B each]
-    return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos) +
-           (lanczos ? (size_t)kTWMax * 32 * 144 : 0);
+    // ctrl | packed tile | map_y | [gray] | map_x | raw x2 | pair records
+    return (size_t)tiled_off_raw(scores, th, col_only) + 2 * tiled_raw_bytes(rows_max, bw_max) + tiled_pairs_bytes(rows_max, bw_max, lanczos);
 }
 
 // Halo pixel of thread `tid`: 0-31 top, 32-63 bottom, then TH left, TH right.  False if tid has none.
@@ -403,43 +404,44 @@ __device__ __forceinline__ void transform_group(const uint8_t *src, uint8_t *dst
 // the int16 weight pairs of cv2's table row (w0|w1<<16, ..., w6|w7<<16); contiguous record layout (8 B per
 // source pixel).  dst = sat_u8((sum + 2^14) >> 15) exactly as LanczosSampler::finish.
 //
-// Every pixel has its own (fy, fx) row of the weight table (128 B).  Read directly, each of the 8 loads of
-// a warp touches 32 different cache lines; COOP transposes through shared memory instead: 8 coalesced
-// loads fetch the warp's 32 rows (4 whole lines each), 8 STS.128 park them in this warp's staging area
-// (slot pitch 144 B: conflict-free both ways), and every lane reads its own row back with LDS.128.
-constexpr uint32_t kLzSlot = 144;                        // bytes per staged weight row (128 + 16 pad)
-constexpr uint32_t kLzStage = 32 * kLzSlot;              // per warp
+// Every pixel has its own (fy, fx) row of the weight table (128 B).  Round 1 fetched it (8 coalesced loads per warp, a
+// transposition through 18 KB of shared memory, 8 LDS.128 per pixel: 64 of the kernel's 204 shared-memory wavefronts per 32
+// pixels, with the LSU pipe 90 % busy and the issue slots 26 %).  Round 2 COMPUTES the 64 weights in registers from what the
+// table is made of (x360_tables.hpp): it[r][c] = sat_s16(rint(f32(k[fy][r] * k[fx][c]) * 2^15)), plus the residue the table's
+// sum-to-2^15 fix-up puts on one of the taps (4..5, 4..5).  FMUL.RN gives the float32 product; FFMA(p, 2^15, 1.5 * 2^23)
+// rounds p * 2^15 (exact) to the nearest even integer in the low mantissa bits — the low 16 bits ARE the int16 weight, and a
+// PRMT packs two of them.  The only product that saturates is 1.0 * 1.0 (fy = fx = 0, tap (3, 3)): clamped explicitly.
+__device__ __forceinline__ uint32_t lz_weight_bits(float cy, float cx) { return __float_as_uint(fmaf(__fmul_rn(cy, cx), 32768.0f, 12582912.0f)); }
 
-template <bool COOP>
-__device__ __forceinline__ uint32_t lanczos_pairs(uint8_t *dsm, uint32_t a0, uint32_t ppitch, const int16_t *__restrict__ tab,
-                                                  uint32_t tab_off, uint32_t wst, int lane)
+__device__ __forceinline__ uint32_t lanczos_pairs(const uint8_t *dsm, uint32_t a0, uint32_t ppitch, const float *__restrict__ k1,
+                                                  const uint32_t *__restrict__ fix, uint32_t idx)
 {
-    const uint8_t *tb = reinterpret_cast<const uint8_t *>(tab);
-    if (COOP) {
-        uint4 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t off = __shfl_sync(0xffffffffu, tab_off, 4 * j + (lane >> 3));
-            v[j] = __ldg(reinterpret_cast<const uint4 *>(tb + off) + (lane & 7));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4 *>(dsm + wst + (uint32_t)(4 * j + (lane >> 3)) * kLzSlot + 16u * (lane & 7)) = v[j];
-        __syncwarp();
-    }
-    const uint4 *wrow = COOP ? reinterpret_cast<const uint4 *>(dsm + wst + (uint32_t)lane * kLzSlot)
-                             : reinterpret_cast<const uint4 *>(tb + tab_off);
+    const uint32_t fx = idx & 31u, fy = idx >> 5;
+    const float4 xa = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fx)), xb = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fx) + 1);
+    const float4 ya = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fy)), yb = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fy) + 1);
+    const float cx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float cy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+    const uint32_t fw = __ldg(fix + idx);
+    const uint32_t fpos = fw & 3u, fdelta = (uint32_t)((int)fw >> 16);                 // residue as a two's-complement word
     int ab = 0, ag = 0, ar = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r, a0 += ppitch) {
-        const uint4 w = COOP ? wrow[r] : __ldg(wrow + r);
+        uint32_t m[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[c] = lz_weight_bits(cy[r], cx[c]);
+        if (r == 3) m[3] = (uint32_t)min((int)(m[3] - 0x4B400000u), 32767);           // sat_s16: 1.0 * 1.0 * 2^15 = 32768
+        if (r == 4 || r == 5) {                                                        // the fix-up lands on one of the taps (4..5, 4..5)
+            m[4] += (fpos == (uint32_t)((r - 4) * 2)) ? fdelta : 0u;
+            m[5] += (fpos == (uint32_t)((r - 4) * 2 + 1)) ? fdelta : 0u;
+        }
+        const uint32_t w0 = __byte_perm(m[0], m[1], 0x5410), w1 = __byte_perm(m[2], m[3], 0x5410);
+        const uint32_t w2 = __byte_perm(m[4], m[5], 0x5410), w3 = __byte_perm(m[6], m[7], 0x5410);
         const uint2 c0 = *reinterpret_cast<const uint2 *>(dsm + a0), c1 = *reinterpret_cast<const uint2 *>(dsm + a0 + 16);
         const uint2 c2 = *reinterpret_cast<const uint2 *>(dsm + a0 + 32), c3 = *reinterpret_cast<const uint2 *>(dsm + a0 + 48);
-        ab = dp2a_lo_su(w.w, c3.x, dp2a_lo_su(w.z, c2.x, dp2a_lo_su(w.y, c1.x, dp2a_lo_su(w.x, c0.x, ab))));
-        ag = dp2a_hi_su(w.w, c3.x, dp2a_hi_su(w.z, c2.x, dp2a_hi_su(w.y, c1.x, dp2a_hi_su(w.x, c0.x, ag))));
-        ar = dp2a_lo_su(w.w, c3.y, dp2a_lo_su(w.z, c2.y, dp2a_lo_su(w.y, c1.y, dp2a_lo_su(w.x, c0.y, ar))));
+        ab = dp2a_lo_su(w3, c3.x, dp2a_lo_su(w2, c2.x, dp2a_lo_su(w1, c1.x, dp2a_lo_su(w0, c0.x, ab))));
+        ag = dp2a_hi_su(w3, c3.x, dp2a_hi_su(w2, c2.x, dp2a_hi_su(w1, c1.x, dp2a_hi_su(w0, c0.x, ag))));
+        ar = dp2a_lo_su(w3, c3.y, dp2a_lo_su(w2, c2.y, dp2a_lo_su(w1, c1.y, dp2a_lo_su(w0, c0.y, ar))));
     }
-    if (COOP) __syncwarp();                              // the staging area is rewritten by the next pixel row
     return LanczosSampler::finish(ab, ag, ar);
 }
 
@@ -525,7 +527,6 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
     const uint32_t off_hi = off_pairs + tiled_lo_bytes(a.rows_max, a.bw_max);          // bilinear: hi plane after the lo plane
     const uint32_t off_gray2 = off_pairs + (uint32_t)TH * kTile * 3u;                  // RAW + SCORES: second gray tile, then second per-warp sums
     const uint32_t off_wsum2 = off_gray2 + tiled_gray_bytes(TH);
-    const uint32_t wst = off_pairs + tiled_pairs_bytes(a.rows_max, a.bw_max, LZ) + (uint32_t)warp * kLzStage;   // Lanczos4 weight staging
     const uint32_t dsm_s = smem_u32(dsm);
     const uint32_t raw_s = dsm_s + kOffRaw, otile_s = dsm_s + kOffTile;
     const uint32_t mbar_s = dsm_s + kOffCtl + (uint32_t)offsetof(TiledCtrl, mbar);
@@ -770,7 +771,7 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                     if (staged) {
                         const uint32_t rx = (uint32_t)((sxs[k] >> 5) - 3 - x_org), ry = (uint32_t)((sys[k] >> 5) - 3 - y_org);
                         pa[k] = off_pairs + ry * ppitch + rx * 8u;                       // dsm-relative
-                        pb[k] = (uint32_t)((sys[k] & 31) * 32 + (sxs[k] & 31)) * 128u;
+                        pb[k] = (uint32_t)((sys[k] & 31) * 32 + (sxs[k] & 31));              // (fy, fx): index of the weight table row
                     } else {
                         bool dummy = false;
                         const LanczosSampler::Px d = LanczosSampler::make_px(sxs[k], sys[k], g, nullptr, dummy);
@@ -988,12 +989,12 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                   } else if constexpr (LZ) {
 #pragma unroll
                     for (int k = 0; k < kTP; ++k) {
-                        const uint32_t pxl = lanczos_pairs<true>(dsm, pa[k], ppitch, a.lz_tab, pb[k], wst, lane);
+                        const uint32_t pxl = lanczos_pairs(dsm, pa[k], ppitch, a.lz_k1, a.lz_fix, pb[k]);
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
                     }
-                    if (SCORES && hvalid) halo_store_t<TH>(gt, tid, (uint8_t)gray_of(lanczos_pairs<false>(dsm, pa[kTP], ppitch, a.lz_tab, pb[kTP], wst, lane)));
+                    if (SCORES && hvalid) halo_store_t<TH>(gt, tid, (uint8_t)gray_of(lanczos_pairs(dsm, pa[kTP], ppitch, a.lz_k1, a.lz_fix, pb[kTP])));
                   } else {
                     uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u);          // upper / lower pair record, carried down the column
                     uint2 X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);        // second chain (rows 4-7)

@@ -141,6 +141,10 @@ int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, i
  *   x360_focal           f of src/core/geometry.py:141
  */
 int x360_lanczos4_table(int16_t *out_tab);
+/* the same table as the factors the tiled kernel computes its weights from: k1d float32 [32][8] (cv2's 1-D Lanczos-4
+ * coefficients), fix uint32 [1024] (per (fy, fx): bits 0-1 = p, the tap (4 + (p >> 1), 4 + (p & 1)) that the table's
+ * sum-to-2^15 fix-up changed; bits 16-31 = the signed residue it added).  it[r][c] = sat_s16(rint(f32(k[fy][r] k[fx][c]) 2^15)) + fix */
+int x360_lanczos4_factors(float *k1d, uint32_t *fix);
 double x360_focal(int32_t out_w, double fov_deg);
 /*
  * How the tiled bilinear path would organise a plan (host-only, no device needed):

@@ -350,3 +350,29 @@ def test_jpeg_header_matches_the_oracle(x360):
     for (h, w, q) in [(1600, 1600, 95), (48, 64, 75), (1, 1, 100), (2048, 2048, 1), (100, 333, 50)]:
         assert x360.jpeg_header(h, w, q) == c_oracle.jpeg_header(h, w, q), (h, w, q)
     assert len(x360.jpeg_header(16, 16)) == 623
+
+
+def test_lanczos4_factors_rebuild_the_table(x360):
+    """The tiled Lanczos4 kernel computes its 64 weights per pixel from the table's factors instead of loading a table row:
+    float32 products of the 1-D coefficients, x 2^15, round half to even, saturate, plus the one-tap fix-up.  Rebuilt here
+    with numpy float32 arithmetic, the factors give exactly the table (which the oracle pins to cv2)."""
+    from oracle import c_oracle
+    L = x360._capi.lib()
+    k = np.zeros((32, 8), np.float32)
+    fix = np.zeros(1024, np.uint32)
+    x360._capi.check(L.x360_lanczos4_factors(k.ctypes.data, fix.ctypes.data))
+    tab = np.zeros((32, 32, 8, 8), np.int16)
+    x360._capi.check(L.x360_lanczos4_table(tab.ctypes.data))
+    p = (k[:, None, :, None] * k[None, :, None, :]).astype(np.float32)              # [fy][fx][r][c], float32 products
+    magic = np.float32(12582912.0)
+    bits = (p * np.float32(32768.0) + magic).astype(np.float32).view(np.uint32)      # the kernel's FFMA(p, 2^15, 1.5 * 2^23): p * 2^15 is exact
+    v = (bits.astype(np.int64) - 0x4B400000)
+    v = np.minimum(v, 32767)                                                         # only 1.0 * 1.0 saturates
+    pos = (fix & 3).reshape(32, 32)
+    delta = (fix.view(np.int32) >> 16).reshape(32, 32)
+    for q in range(4):
+        v[:, :, 4 + (q >> 1), 4 + (q & 1)] += np.where(pos == q, delta, 0)
+    assert np.array_equal(v.astype(np.int16), tab)
+    assert np.array_equal(tab.reshape(1024, 8, 8), c_oracle.lanczos4_table().reshape(1024, 8, 8))
+    assert (v.reshape(1024, 64).sum(axis=1) == 32768).all()                          # what the fix-up is for
+    assert np.count_nonzero(delta) == 856                                            # SURVEY App. A-3: 856 of 1024 entries are fixed up
