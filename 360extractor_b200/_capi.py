@@ -39,6 +39,18 @@ class Params(ctypes.Structure):
     ]
 
 
+class BlurState(ctypes.Structure):
+    """x360_blur_state (include/x360.h): the accept / reject machine of src/core/processor.py:341-376."""
+    _fields_ = [
+        ("enabled", ctypes.c_int32), ("smart", ctypes.c_int32),
+        ("threshold", ctypes.c_double),
+        ("history", ctypes.c_double * 10),
+        ("hist_len", ctypes.c_int32), ("hist_head", ctypes.c_int32),
+        ("consecutive_skips", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("skipped", ctypes.c_int64), ("forced", ctypes.c_int64),
+    ]
+
+
 # every symbol include/x360.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _sz, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_double
 SYMBOLS = {
@@ -69,6 +81,9 @@ SYMBOLS = {
     "x360_jpeg_coefficients_host": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "x360_jpeg_header": (ctypes.c_int, [_i32, _i32, _i32, _vp, _i32]),
     "x360_extract_host_jpeg": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "x360_blur_state_init": (None, [ctypes.POINTER(BlurState), _i32, _i32, _dbl]),
+    "x360_blur_accept": (ctypes.c_int, [ctypes.POINTER(BlurState), _dbl]),
+    "x360_extract_host_filtered": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(BlurState), _vp, _i64, _vp, _vp, ctypes.POINTER(_i64)]),
     "x360_host_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp)]),
     "x360_host_free": (ctypes.c_int, [_vp]),
     "x360_last_error": (ctypes.c_char_p, []),

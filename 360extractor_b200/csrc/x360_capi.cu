@@ -70,6 +70,30 @@ inline int lab_int(const char *name, int dflt) { const char *e = lab_env(name); 
 // own size, which would lower it under another live plan.
 constexpr int kTiledSmemCap = 110 * 1024;
 
+// Device scratch of the one-shot entries (x360_remap_maps, x360_blur_sums, x360_make_maps: INTEGRATION.md option A, called once
+// per view by a host that keeps the reference's loop): grow-only buffers kept per thread and device instead of a cudaMalloc /
+// cudaFree pair per call (each costs a device synchronisation).
+struct ScratchSlot { void *p = nullptr; size_t cap = 0; int device = -1; };
+void *scratch_get(int slot, int device, size_t bytes)
+{
+    thread_local ScratchSlot slots[6];
+    ScratchSlot &s = slots[slot];
+    if (s.p && (s.device != device || s.cap < bytes)) {
+        cudaSetDevice(s.device);
+        cudaFree(s.p);
+        cudaSetDevice(device);
+        s.p = nullptr;
+        s.cap = 0;
+    }
+    if (!s.p) {
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMalloc(&s.p, want) != cudaSuccess) { cudaGetLastError(); s.p = nullptr; return nullptr; }
+        s.cap = want;
+        s.device = device;
+    }
+    return s.p;
+}
+
 // geometry.py:141 — f = (0.5*dest_w) / tan(0.5*radians(fov_deg)); radians(x) = x*(pi/180)
 double focal_of(int out_w, double fov_deg)
 {
@@ -556,6 +580,7 @@ struct x360_plan {
     x360_jpeg *jpeg = nullptr;
     uint8_t *d_jpeg[2] = {};
     long long *d_joff[2] = {}, *h_joff[2] = {};
+    long long *h_sums[2] = {};           // filtered host path: the chunk's sum pairs, pinned
     long long jpeg_cap = 0;
     cudaStream_t s_off = nullptr;
     cudaEvent_t ev_off[2] = {};
@@ -1102,6 +1127,7 @@ int x360_plan_destroy(x360_plan *pl)
         cudaFree(pl->d_jpeg[i]);
         cudaFree(pl->d_joff[i]);
         if (pl->h_joff[i]) cudaFreeHost(pl->h_joff[i]);
+        if (pl->h_sums[i]) cudaFreeHost(pl->h_sums[i]);
         if (pl->ev_off[i]) cudaEventDestroy(pl->ev_off[i]);
     }
     if (pl->s_off) cudaStreamDestroy(pl->s_off);
@@ -1301,15 +1327,14 @@ int x360_make_maps(x360_plan *pl, int32_t view, float *map_x, float *map_y)
     if (view < 0 || view >= pl->p.n_views) return fail(X360_E_INVALID, "view %d out of range", view);
     CU(cudaSetDevice(pl->p.device));
     const size_t n = (size_t)pl->g.ow * pl->g.oh;
-    float *d = nullptr;
-    CU(cudaMalloc(&d, sizeof(float) * 2 * n));
+    float *d = (float *)scratch_get(0, pl->p.device, sizeof(float) * 2 * n);
+    if (!d) return fail(X360_E_NOMEM, "out of device memory for the maps");
     const dim3 grid((pl->g.ow + 31) / 32, (pl->g.oh + 7) / 8);
     make_maps_kernel<<<grid, 256>>>(pl->g, pl->d_R + 9 * view, d, d + n);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(map_x, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(map_y, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost);
-    cudaFree(d);
     if (e != cudaSuccess) return fail(X360_E_CUDA, "make_maps failed: %s", cudaGetErrorString(e));
     return X360_OK;
 }
@@ -1326,19 +1351,18 @@ int x360_remap_maps(int32_t device, const uint8_t *src, int32_t src_h, int32_t s
     CU(cudaSetDevice(device));
     const Geom g = make_geom(src_w, src_h, out_w, out_h, 90.0);
     const size_t sb = (size_t)src_h * src_w * 3, n = (size_t)out_h * out_w;
-    uint8_t *d_src = nullptr, *d_dst = nullptr;
-    float *d_map = nullptr;
+    uint8_t *d_src = (uint8_t *)scratch_get(1, device, sb), *d_dst = (uint8_t *)scratch_get(2, device, n * 3);
+    float *d_map = (float *)scratch_get(3, device, sizeof(float) * 2 * n);
     int16_t *d_tab = nullptr;
-    cudaError_t e = cudaMalloc(&d_src, sb);
-    if (e == cudaSuccess) e = cudaMalloc(&d_dst, n * 3);
-    if (e == cudaSuccess) e = cudaMalloc(&d_map, sizeof(float) * 2 * n);
-    if (e == cudaSuccess) e = cudaMemcpy(d_src, src, sb, cudaMemcpyHostToDevice);
+    if (!d_src || !d_dst || !d_map) return fail(X360_E_NOMEM, "out of device memory");
+    cudaError_t e = cudaMemcpy(d_src, src, sb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_map, map_x, sizeof(float) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_map + n, map_y, sizeof(float) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && interp == X360_INTERP_LANCZOS4) {
+        d_tab = (int16_t *)scratch_get(4, device, 1024 * 64 * sizeof(int16_t));
+        if (!d_tab) return fail(X360_E_NOMEM, "out of device memory");
         const std::vector<int16_t> t = lanczos4_q15_table();
-        e = cudaMalloc(&d_tab, t.size() * sizeof(int16_t));
-        if (e == cudaSuccess) e = cudaMemcpy(d_tab, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(d_tab, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess) {
         const dim3 grid((out_w + 31) / 32, (out_h + 7) / 8);
@@ -1350,7 +1374,6 @@ int x360_remap_maps(int32_t device, const uint8_t *src, int32_t src_h, int32_t s
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(dst, d_dst, n * 3, cudaMemcpyDeviceToHost);
-    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_map); cudaFree(d_tab);
     if (e != cudaSuccess) return fail(X360_E_CUDA, "remap_maps failed: %s", cudaGetErrorString(e));
     return X360_OK;
 }
@@ -1365,19 +1388,15 @@ int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, i
         return fail(X360_E_CUDA, "no CUDA device available (libx360 has no CPU fallback)");
     CU(cudaSetDevice(device));
     const size_t n = (size_t)h * w;
-    uint8_t *d_img = nullptr, *d_gray = nullptr;
-    long long *d_s = nullptr;
-    cudaError_t e = cudaMalloc(&d_img, n * channels);
-    if (e == cudaSuccess) e = cudaMalloc(&d_s, sizeof(long long) * 2);
-    if (e == cudaSuccess) e = cudaMemset(d_s, 0, sizeof(long long) * 2);
+    uint8_t *d_img = (uint8_t *)scratch_get(1, device, n * channels), *d_gray = channels == 3 ? (uint8_t *)scratch_get(2, device, n) : nullptr;
+    long long *d_s = (long long *)scratch_get(5, device, sizeof(long long) * 2);
+    if (!d_img || !d_s || (channels == 3 && !d_gray)) return fail(X360_E_NOMEM, "out of device memory");
+    cudaError_t e = cudaMemset(d_s, 0, sizeof(long long) * 2);
     if (e == cudaSuccess) e = cudaMemcpy(d_img, image, n * channels, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && channels == 3) {
-        e = cudaMalloc(&d_gray, n);
-        if (e == cudaSuccess) {
-            gray_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_img, d_gray, n);
-            g_launches.fetch_add(1);
-            e = cudaGetLastError();
-        }
+        gray_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_img, d_gray, n);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
         size_t blocks = (n + 255) / 256;
@@ -1388,7 +1407,6 @@ int x360_blur_sums(int32_t device, const uint8_t *image, int32_t h, int32_t w, i
     }
     long long hs[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpy(hs, d_s, sizeof hs, cudaMemcpyDeviceToHost);
-    cudaFree(d_img); cudaFree(d_gray); cudaFree(d_s);
     if (e != cudaSuccess) return fail(X360_E_CUDA, "blur_sums failed: %s", cudaGetErrorString(e));
     *sum_lap = hs[0];
     *sum_lap2 = hs[1];
@@ -1777,6 +1795,130 @@ int x360_extract_host_jpeg(x360_plan *pl, const uint8_t *frames, int32_t n_frame
     const std::string first_error = rc != X360_OK ? g_err : std::string();
     const cudaError_t e_out = cudaStreamSynchronize(pl->s_out), e_off = cudaStreamSynchronize(pl->s_off), e_k = cudaStreamSynchronize(pl->s_k),
                       e_in = cudaStreamSynchronize(pl->s_in);
+    if (rc != X360_OK) { g_err = first_error; return rc; }
+    for (cudaError_t e : {e_out, e_off, e_k, e_in})
+        if (e != cudaSuccess) return fail(X360_E_CUDA, "pipelined extraction failed: %s", cudaGetErrorString(e));
+    return X360_OK;
+}
+
+// ---- the blur accept / reject machine (processor.py:341-376) and the filtered download --------------------------------
+void x360_blur_state_init(x360_blur_state *st, int32_t enabled, int32_t smart, double threshold)
+{
+    if (!st) return;
+    memset(st, 0, sizeof *st);
+    st->enabled = enabled != 0;
+    st->smart = smart != 0;
+    st->threshold = threshold;
+}
+
+int x360_blur_accept(x360_blur_state *st, double score)
+{
+    if (!st || !st->enabled) return 1;                         // processor.py:341 — no score, view always kept
+    bool blurry = false;
+    if (st->smart) {
+        if (score < st->threshold) blurry = true;              // 1. floor
+        else if (st->hist_len > 0) {                           // 2. adaptive check against the rolling mean (sum in deque order)
+            double sum = 0.0;
+            for (int i = 0; i < st->hist_len; ++i) sum += st->history[(st->hist_head + i) % 10];
+            if (score < (sum / (double)st->hist_len) * 0.6) blurry = true;
+        }
+        if (blurry) {                                          // 3. safety override
+            if (++st->consecutive_skips > 5) {
+                blurry = false;
+                st->consecutive_skips = 0;
+                st->forced++;
+            }
+        }
+        if (!blurry) {                                         // 4. accepted scores feed the history (deque(maxlen=10))
+            st->consecutive_skips = 0;
+            if (st->hist_len < 10) st->history[(st->hist_head + st->hist_len++) % 10] = score;
+            else { st->history[st->hist_head] = score; st->hist_head = (st->hist_head + 1) % 10; }
+        }
+    } else {
+        blurry = score < st->threshold;                        // standard mode, processor.py:369-371
+    }
+    if (blurry) st->skipped++;
+    return blurry ? 0 : 1;
+}
+
+int x360_extract_host_filtered(x360_plan *pl, const uint8_t *frames, int32_t n_frames, x360_blur_state *state, uint8_t *out_views,
+                               int64_t capacity_views, uint8_t *keep, double *scores, int64_t *n_kept)
+{
+    if (!pl || !frames || !out_views || !state || !keep || !n_kept) return fail(X360_E_INVALID, "null argument");
+    if (n_frames < 0 || capacity_views < 0) return fail(X360_E_INVALID, "negative frame count or capacity");
+    *n_kept = 0;
+    if (n_frames == 0) return X360_OK;
+    CU(cudaSetDevice(pl->p.device));
+    if (int rc = pipe_setup(pl)) return rc;
+    const int V = pl->p.n_views, per = pl->chunk * V;
+    const bool scoring = state->enabled != 0;
+    if (!pl->s_off) CU(cudaStreamCreateWithFlags(&pl->s_off, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!pl->h_sums[i]) CU(cudaHostAlloc(&pl->h_sums[i], sizeof(long long) * 2 * (size_t)per, cudaHostAllocDefault));
+        if (!pl->ev_off[i]) CU(cudaEventCreateWithFlags(&pl->ev_off[i], cudaEventDisableTiming));
+    }
+    const size_t fb = (size_t)pl->g.H * pl->g.W * 3, v1 = (size_t)pl->g.oh * pl->g.ow * 3;
+    const double N = (double)pl->g.oh * (double)pl->g.ow;
+    long long kept = 0;
+    int rc = X360_OK;
+    const uint8_t *d_result[2] = {nullptr, nullptr};
+    // finish chunk c: its sums are on the host -> replay the machine in (frame, view) order -> one download per kept view
+    auto finish = [&](int c) -> int {
+        const int b = c & 1, f0 = c * pl->chunk, n = std::min(pl->chunk, n_frames - f0), m = n * V;
+        if (scoring) CU(cudaEventSynchronize(pl->ev_off[b]));
+        CU(cudaStreamWaitEvent(pl->s_out, pl->ev_k[b], 0));              // the chunk's kernels (a no-op after the host wait above)
+        const long long *hs = pl->h_sums[b], *hs2 = pl->h_sums[b] + per;
+        for (int i = 0; i < m; ++i) {
+            double sc = 0.0;
+            if (scoring) {                                     // ndarray.var: s2/N - (s/N)^2 in fp64 (image_utils.py:27)
+                const double mean = (double)hs[i] / N;
+                sc = (double)hs2[i] / N - mean * mean;
+            }
+            if (scores) scores[(size_t)f0 * V + i] = sc;
+            const int k = x360_blur_accept(state, sc);
+            keep[(size_t)f0 * V + i] = (uint8_t)k;
+            if (!k) continue;
+            if (kept >= capacity_views) return fail(X360_E_NOMEM, "more kept views than the %lld the output holds", (long long)capacity_views);
+            CU(cudaMemcpyAsync(out_views + (size_t)kept * v1, d_result[b] + (size_t)i * v1, v1, cudaMemcpyDeviceToHost, pl->s_out));
+            ++kept;
+        }
+        CU(cudaEventRecord(pl->ev_out[b], pl->s_out));
+        return X360_OK;
+    };
+    const int n_chunks = (n_frames + pl->chunk - 1) / pl->chunk;
+    for (int c = 0; c < n_chunks && rc == X360_OK; ++c) {
+        const int b = c & 1, f0 = c * pl->chunk, n = std::min(pl->chunk, n_frames - f0), m = n * V;
+        auto enqueue = [&]() -> int {
+            if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
+            CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+            CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
+            CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
+            if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));       // the kept views of chunk c-2 have left this buffer
+            long long *ds = scoring ? pl->d_sums[b] : nullptr;
+            long long *ds2 = scoring ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
+            if (int r = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return r;
+            d_result[b] = pl->d_views[b];
+            if (pl->sharpen) {
+                if (int r = unsharp_launch(pl->d_views[b], (long long)m, pl->g.oh, pl->g.ow, pl->sharpen_strength, pl->d_sharp[b], pl->s_k)) return r;
+                d_result[b] = pl->d_sharp[b];
+            }
+            CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
+            if (scoring) {
+                CU(cudaStreamWaitEvent(pl->s_off, pl->ev_k[b], 0));
+                CU(cudaMemcpyAsync(pl->h_sums[b], ds, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
+                CU(cudaMemcpyAsync(pl->h_sums[b] + per, ds2, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
+                CU(cudaEventRecord(pl->ev_off[b], pl->s_off));
+            }
+            return X360_OK;
+        };
+        rc = enqueue();
+        if (rc == X360_OK && c >= 1) rc = finish(c - 1);
+    }
+    if (rc == X360_OK) rc = finish(n_chunks - 1);
+    const std::string first_error = rc != X360_OK ? g_err : std::string();
+    const cudaError_t e_out = cudaStreamSynchronize(pl->s_out), e_off = cudaStreamSynchronize(pl->s_off), e_k = cudaStreamSynchronize(pl->s_k),
+                      e_in = cudaStreamSynchronize(pl->s_in);
+    *n_kept = kept;
     if (rc != X360_OK) { g_err = first_error; return rc; }
     for (cudaError_t e : {e_out, e_off, e_k, e_in})
         if (e != cudaSuccess) return fail(X360_E_CUDA, "pipelined extraction failed: %s", cudaGetErrorString(e));

@@ -193,6 +193,24 @@ class Extractor:
         check(lib().x360_extract_host(self._plan, ptr(frames), F, ptr(out), ptr(s), ptr(s2)))
         return out, s, s2
 
+    def extract_filtered(self, frames, state, out=None):
+        """The pipelined host path that downloads only the views the blur machine keeps (``state``: a ``_capi.BlurState``
+        carried across calls, as the reference carries ``blur_history`` / ``consecutive_blur_skips`` across frames,
+        src/core/processor.py:224-225,341-376).  Returns ``(kept_views uint8 [K][d][d][3], keep bool [F][V], scores float64
+        [F][V] or None)``; rejected views never cross PCIe."""
+        frames, F = self._host_frames(frames)
+        n = F * self.n_views
+        if out is None:
+            out = np.empty((n, self.out_h, self.out_w, 3), np.uint8)
+        elif out.dtype != np.uint8 or not out.flags.c_contiguous or out.shape[1:] != (self.out_h, self.out_w, 3):
+            raise ValueError("out must be a C-contiguous uint8 array [capacity][d][d][3]")
+        keep = np.zeros(n, np.uint8)
+        scores = np.zeros(n, np.float64)
+        k = ctypes.c_int64(0)
+        check(lib().x360_extract_host_filtered(self._plan, ptr(frames), F, ctypes.byref(state), ptr(out), int(out.shape[0]), ptr(keep), ptr(scores),
+                                               ctypes.byref(k)))
+        return out[: k.value], keep.reshape(F, self.n_views).astype(bool), (scores.reshape(F, self.n_views) if state.enabled else None)
+
     def jpeg_capacity(self, n_frames):
         """Bytes that always hold the files of ``n_frames`` frames (the raw size of the views plus headers)."""
         return n_frames * self.n_views * (self.out_h * self.out_w * 3 + 1024)

@@ -44,7 +44,10 @@ class ExtractionSession:
         if layout_mode == "adaptive":                                   # legacy alias, processor.py:170-171
             layout_mode = "ring"
         self.interpolation_mode = settings.get("interpolation_mode", "linear")
-        self.blur = BlurFilter.from_settings(settings)
+        self.blur = BlurFilter.from_settings(settings)           # host replay (sharded / encoded paths); process() uses the library's copy
+        from ._capi import BlurState, lib
+        self._blur_state = BlurState()
+        lib().x360_blur_state_init(self._blur_state, int(self.blur.enabled), int(self.blur.smart), float(self.blur.threshold))
         self.sharpen_enabled = settings.get("sharpening_enabled", False)   # processor.py:228
         self.sharpen_strength = settings.get("sharpening_strength", 0.5)   # processor.py:229
         self.device = int(device)
@@ -89,14 +92,22 @@ class ExtractionSession:
         return self.extractor.extract(frames, want_scores=self.blur.enabled)
 
     def process(self, frames) -> List[ViewResult]:
-        """Batch equivalent of the per-frame view loop: returns the kept views in (frame, view) order."""
-        views, scores = self.extract_batch(frames)
+        """Batch equivalent of the per-frame view loop: returns the kept views in (frame, view) order.
+
+        With the blur filter on, the accept / reject machine runs inside the library's pipeline (``x360_extract_host_filtered``:
+        the scores of a chunk come back first, the machine is replayed in (frame, view) order, only the kept views are
+        downloaded); its state lives in ``self._blur_state`` across calls, as the reference's does across frames."""
+        if self.extractor is None:
+            return []
+        kept_views, keep, scores = self.extractor.extract_filtered(frames, self._blur_state)
+        self.blur.skipped, self.blur.forced = int(self._blur_state.skipped), int(self._blur_state.forced)
         kept: List[ViewResult] = []
-        for f in range(views.shape[0]):
+        i = 0
+        for f in range(keep.shape[0]):
             for v, name in enumerate(self.names):
-                score = float(scores[f, v]) if scores is not None else None
-                if self.blur.accept(score):
-                    kept.append(ViewResult(f, name, views[f, v], score))
+                if keep[f, v]:
+                    kept.append(ViewResult(f, name, kept_views[i], float(scores[f, v]) if scores is not None else None))
+                    i += 1
         return kept
 
     def process_encoded(self, frames, quality=None):

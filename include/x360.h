@@ -251,6 +251,34 @@ int x360_jpeg_header(int32_t h, int32_t w, int32_t quality, uint8_t *out, int32_
 int x360_extract_host_jpeg(x360_plan *plan, const uint8_t *frames, int32_t n_frames, int32_t quality, uint8_t *out,
                            int64_t out_capacity, int64_t *offsets, int64_t *sum_lap, int64_t *sum_lap2);
 
+/*
+ * The blur accept / reject machine of src/core/processor.py:341-376 (state: blur_history = deque(maxlen=10) and
+ * consecutive_blur_skips, processor.py:224-225; settings blur_filter_enabled / smart_blur_enabled / blur_threshold,
+ * processor.py:219-221), as plain C so that the pipelined host path can decide per view which pixels to download.
+ * x360_blur_accept returns 1 when the view is kept; the state carries across views AND frames in iteration order.
+ */
+typedef struct x360_blur_state {
+    int32_t enabled, smart;
+    double threshold;
+    double history[10];          /* accepted scores, oldest first from history[head] (ring buffer) */
+    int32_t hist_len, hist_head;
+    int32_t consecutive_skips;
+    int32_t reserved;
+    int64_t skipped, forced;
+} x360_blur_state;
+void x360_blur_state_init(x360_blur_state *state, int32_t enabled, int32_t smart, double threshold);
+int x360_blur_accept(x360_blur_state *state, double score);
+/*
+ * x360_extract_host that downloads only the views the blur machine keeps: per chunk the Laplacian sums come back first
+ * (a few bytes), the machine is replayed on the host in (frame, view) order, and one copy per KEPT view is queued — rejected
+ * views never cross PCIe.  out_views: the kept views back to back, at most capacity_views of them; keep: uint8
+ * [n_frames * n_views] (1 = kept); scores: float64 [n_frames * n_views] (may be NULL); n_kept: their count.  With the
+ * machine disabled (state->enabled == 0) every view is kept and no score is computed, as in processor.py:341.
+ * Sharpening (x360_plan_set_sharpen) applies to what is downloaded, after the decision, as in processor.py:379-381.
+ */
+int x360_extract_host_filtered(x360_plan *plan, const uint8_t *frames, int32_t n_frames, x360_blur_state *state,
+                               uint8_t *out_views, int64_t capacity_views, uint8_t *keep, double *scores, int64_t *n_kept);
+
 /* pinned host memory for the pipelined path (cudaHostAlloc / cudaFreeHost) */
 int x360_host_alloc(size_t bytes, void **out_ptr);
 int x360_host_free(void *ptr);

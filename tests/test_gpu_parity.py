@@ -361,6 +361,29 @@ def test_session_reproduces_the_reference_worker(x360, name):
             assert k.score == pytest.approx(table[k.frame_index, names.index(k.camera)], rel=SCORE_RTOL, abs=1e-9)
 
 
+def test_filtered_download_keeps_state_across_calls(x360):
+    """ExtractionSession.process downloads only the kept views (x360_extract_host_filtered) and carries the machine's state
+    across calls exactly as one call over the whole clip does; the disabled filter keeps everything without scoring."""
+    import json
+    with open(os.path.join(GOLDEN, "worker_cases.json")) as f:
+        case = json.load(f)["scenarios"]["smart_ring4"]
+    frames = np.load(os.path.join(GOLDEN, "worker_clip.npz"))["frames"]
+    with x360.ExtractionSession(dict(case["settings"]), frames.shape[1], frames.shape[2], max_batch=2) as sess:
+        whole = sess.process(frames)
+        skipped, forced = sess.blur.skipped, sess.blur.forced
+    with x360.ExtractionSession(dict(case["settings"]), frames.shape[1], frames.shape[2], max_batch=3) as sess:
+        parts = []
+        for lo in (0, 5, 6, 11):
+            hi = {0: 5, 5: 6, 6: 11, 11: len(frames)}[lo]
+            parts += [(lo + k.frame_index, k.camera, sha(k.image)) for k in sess.process(frames[lo:hi])]
+        assert (sess.blur.skipped, sess.blur.forced) == (skipped, forced) and forced >= 1
+    assert parts == [(k.frame_index, k.camera, sha(k.image)) for k in whole]
+    off = dict(case["settings"], blur_filter_enabled=False)
+    with x360.ExtractionSession(off, frames.shape[1], frames.shape[2]) as sess:
+        everything = sess.process(frames[:3])
+    assert len(everything) == 3 * 4 and all(k.score is None for k in everything)
+
+
 def test_blur_analyzer_mirrors_reference(x360, oracle):
     """BlurAnalyzer.analyze_frame = src/core/analyzer.py:44-76: ring layout whatever layout_mode says,
     bilinear, resolution default 1024; scores from the fused kernel == the oracle's to 1e-12."""
@@ -377,6 +400,33 @@ def test_blur_analyzer_mirrors_reference(x360, oracle):
     assert res["average"] == pytest.approx(sum(want) / 5, rel=SCORE_RTOL)
     assert res["min"] == pytest.approx(min(want), rel=SCORE_RTOL) and res["max"] == pytest.approx(max(want), rel=SCORE_RTOL)
     assert all(isinstance(sc, float) for _, sc in res["details"])
+
+
+LZ_COL_CASES = [
+    # (H, W, d, fov, n, F): Lanczos4 on yaw-only plans (a thread's pixels read the same source columns; weights computed in registers)
+    (512, 1024, 256, 90, 8, 3),        # 1.27 source px per output px
+    (720, 1440, 200, 90, 4, 2),        # 2.3: windows 2.3 rows apart, partial tiles (200 = 6 x 32 + 8)
+    (300, 600, 250, 60, 3, 2),         # magnification: consecutive pixels share all eight rows; frame pitch not a multiple of 16 B
+    (1440, 2880, 333, 100, 5, 1),      # odd size, seam view at yaw 144 / 216
+    (480, 960, 64, 120, 2, 2),         # 4.3 source px per output px: beyond the staging capacity on most tiles
+]
+
+
+@pytest.mark.parametrize("scores", [False, True], ids=["noscores", "fused-score"])
+@pytest.mark.parametrize("cfg", LZ_COL_CASES)
+def test_lanczos_ring_plans(x360, oracle, cfg, scores):
+    H, W, d, fov, n, F = cfg
+    frames = np.stack([noise_frame(700 + i, H, W) for i in range(F)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(n, 0, "ring"))
+    assert x360.column_only_map_x(R)
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, 1, want_scores=scores)
+    with x360.Extractor(H, W, d, fov, R, "lanczos", max_batch=F, flags=x360.FLAG_FUSED_SCORE if scores else 0) as ex:
+        if scores:
+            got, s, s2 = ex.extract_sums(frames)
+            assert np.array_equal(s, ws) and np.array_equal(s2, ws2), "integer Laplacian sums"
+        else:
+            got, _ = ex.extract(frames, want_scores=False)
+    assert_same(got, want, f"{cfg} lanczos ring", LANCZOS_TOL_LSB)
 
 
 # ---- plan variants and robustness of the host side ----------------------------------------------

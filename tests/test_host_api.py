@@ -376,3 +376,30 @@ def test_lanczos4_factors_rebuild_the_table(x360):
     assert np.array_equal(tab.reshape(1024, 8, 8), c_oracle.lanczos4_table().reshape(1024, 8, 8))
     assert (v.reshape(1024, 64).sum(axis=1) == 32768).all()                          # what the fix-up is for
     assert np.count_nonzero(delta) == 856                                            # 856 of 1024 entries are fixed up
+
+
+def test_c_blur_machine_equals_the_python_replay(x360):
+    """x360_blur_accept (the machine inside x360_extract_host_filtered) makes the same decisions as BlurFilter — which
+    test_blur_machine_reproduces_the_reference_worker pins to the reference's loop — on the recorded scores and on random ones."""
+    cap = x360._capi
+    L = cap.lib()
+
+    def run_c(scores, enabled, smart, th):
+        st = cap.BlurState()
+        L.x360_blur_state_init(st, enabled, smart, th)
+        return [bool(L.x360_blur_accept(st, float(s))) for s in scores], int(st.skipped), int(st.forced)
+
+    for name, case in _worker_cases()["scenarios"].items():
+        scores = [float.fromhex(h) for h in case["scores_in_call_order"]]
+        f = x360.BlurFilter.from_settings(case["settings"])
+        want = [f.accept(s) for s in scores]
+        assert run_c(scores, int(f.enabled), int(f.smart), float(f.threshold)) == (want, f.skipped, f.forced), name
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        scores = np.concatenate([rng.uniform(0, 500, rng.integers(1, 60)), rng.uniform(0, 30, rng.integers(0, 20)), rng.uniform(100, 900, rng.integers(0, 40))])
+        rng.shuffle(scores)
+        for smart in (0, 1):
+            th = float(rng.uniform(10, 300))
+            f = x360.BlurFilter(True, bool(smart), th)
+            want = [f.accept(float(s)) for s in scores]
+            assert run_c(scores, 1, smart, th) == (want, f.skipped, f.forced)
