@@ -373,7 +373,7 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
     traffic, traffic_src = measured_traffic(f"{name}:F{F}:{kernel_name}")
     n_tv = max(1, sum(modes.values()))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                "traffic": traffic, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full; a step of several launches: their sum)",
                 "traffic_source": traffic_src, "algorithmic_gb_per_launch": F * b_alg_frame / 1e9, "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg_frame,
                 "touched_source_pixels_per_frame": U, "bytes_per_output_pixel": b_alg_frame / (V * d * d),
                 "kernel": kernel_name, "launches_per_step": launches / max(1, steps),
