@@ -184,11 +184,39 @@ blur_sums_views_kernel(const uint8_t *__restrict__ views, int h, int w, int fast
 // Needs w % 4 == 0, a 4-byte aligned base, w >= 8 and h >= 2 (anything else takes blur_sums_views_kernel).
 constexpr int kScRows = 32, kScStride = 120, kScWarps = 8;
 
-__device__ __forceinline__ uint32_t gray4_of(uint32_t w0, uint32_t w1, uint32_t w2)      // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+// Four packed BGR pixels (B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3) -> their four gray bytes.  The Q15 weights are doubled so that
+// the gray value ((3735 B + 19235 G + 9798 R + 2^14) >> 15, see gray_of) is byte 2 of the accumulator, and placed per pixel
+// position so that no pixel has to be realigned first: 8 DP2A + 3 PRMT.
+__device__ __forceinline__ uint32_t gray4_of(uint32_t w0, uint32_t w1, uint32_t w2)
 {
-    const uint32_t g0 = gray_of(w0), g1 = gray_of(__byte_perm(w0, w1, 0x0543));
-    const uint32_t g2 = gray_of(__byte_perm(w1, w2, 0x0432)), g3 = gray_of(w2 >> 8);
-    return __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
+    constexpr uint32_t kB = 2 * 3735u, kG = 2 * 19235u, kR = 2 * 9798u;
+    uint32_t a0 = 32768u, a1 = 32768u, a2 = 32768u, a3 = 32768u;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a0) : "r"(kB | (kG << 16)), "r"(w0));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(a0) : "r"(kR), "r"(w0));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(a1) : "r"(kB << 16), "r"(w0));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a1) : "r"(kG | (kR << 16)), "r"(w1));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(a2) : "r"(kB | (kG << 16)), "r"(w1));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a2) : "r"(kR), "r"(w2));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a3) : "r"(kB << 16), "r"(w2));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(a3) : "r"(kG | (kR << 16)), "r"(w2));
+    return __byte_perm(__byte_perm(__byte_perm(a0, a1, 0x0062), a2, 0x0610), a3, 0x6210);
+}
+
+// One row of a lane's four pixels: C = this row's gray word, U / D the rows above / below; the left / right neighbours are
+// bytes of the adjacent lanes' words, picked by per-lane PRMT selectors (which also encode the reflect-101 image edges).
+__device__ __forceinline__ void march_row(uint32_t U, uint32_t C, uint32_t D, uint32_t sel_l, uint32_t sel_r, int &pl, unsigned &pl2)
+{
+    const uint32_t up = __shfl_up_sync(0xffffffffu, C, 1), dn = __shfl_down_sync(0xffffffffu, C, 1);
+    const uint32_t Lw = __byte_perm(C, up, sel_l);                // [l, c0, c1, c2]
+    const uint32_t Rw = __byte_perm(C, dn, sel_r);                // [c1, c2, c3, r]
+    constexpr uint32_t kA = 0x0001fc01u;                          // [ 1, -4,  1,  0]
+    constexpr uint32_t kB = 0x01fc0100u;                          // [ 0,  1, -4,  1]
+    const int L0 = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
+    const int L1 = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
+    const int L2 = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
+    const int L3 = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
+    pl += L0 + L1 + L2 + L3;
+    pl2 += (unsigned)(L0 * L0) + (unsigned)(L1 * L1) + (unsigned)(L2 * L2) + (unsigned)(L3 * L3);
 }
 
 __global__ void __launch_bounds__(32 * kScWarps)
@@ -199,59 +227,72 @@ blur_sums_march_kernel(const uint8_t *__restrict__ views, int h, int w, long lon
     const int x = (int)blockIdx.x * kScStride - 4 + 4 * lane;                 // this lane's four pixels x .. x+3
     const int r0 = ((int)blockIdx.y * kScWarps + warp) * kScRows, r1 = min(r0 + kScRows, h);
     const bool live = x >= 0 && x < w;
-    const uint32_t *img = reinterpret_cast<const uint32_t *>(views + (size_t)blockIdx.z * h * w * 3);
-    const size_t pitch_w = (size_t)w * 3 / 4;                                 // words per row
-    const size_t col_w = live ? (size_t)x * 3 / 4 : 0;
+    const bool counts = live && lane > 0 && lane < 31;                        // lanes 0 / 31: halo providers
+    // lanes outside the image walk column 0: their sums are dropped at the end
+    const uint8_t *col = views + (size_t)blockIdx.z * h * w * 3 + (live ? (size_t)x * 3 : 0);
+    const unsigned pitch = (unsigned)w * 3u;                                  // bytes per row (32-bit: one IMAD.WIDE per row address)
+    const uint32_t sel_l = x == 0 ? 0x2101u : 0x2107u;                        // g[-1] = g[1]; else byte 3 of the lane on the left
+    const uint32_t sel_r = x + 3 == w - 1 ? 0x2321u : 0x4321u;                // g[w] = g[w-2]; else byte 0 of the lane on the right
     int pl = 0;
     unsigned pl2 = 0;
     if (r0 < h) {
         auto load_row = [&](int y, uint32_t (&r)[3]) {
-            const uint32_t *src = img + (size_t)y * pitch_w + col_w;
-            r[0] = live ? __ldg(src) : 0u; r[1] = live ? __ldg(src + 1) : 0u; r[2] = live ? __ldg(src + 2) : 0u;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(col + (size_t)((unsigned)min(y, h - 1) * (unsigned long long)pitch));
+            r[0] = __ldg(src); r[1] = __ldg(src + 1); r[2] = __ldg(src + 2);
         };
         // rows are loaded four at a time, one group ahead of the group being summed: 2 x 4 x 12 bytes per lane in flight
-        uint32_t ra[3], rb[3], cur[4][3], nxt[4][3];
+        uint32_t ra[3], rb[3], ga[4][3], gb[4][3];
         load_row(r0 == 0 ? 1 : r0 - 1, ra);
         load_row(r0, rb);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) load_row(min(r0 + 1 + j, h - 1), cur[j]);
+        for (int j = 0; j < 4; ++j) load_row(r0 + 1 + j, ga[j]);
         uint32_t U = gray4_of(ra[0], ra[1], ra[2]), C = gray4_of(rb[0], rb[1], rb[2]);
-        const bool counts = live && lane > 0 && lane < 31;                    // lanes 0 / 31: halo providers
-        const bool at_left = x == 0, at_right = x + 3 == w - 1;
-#pragma unroll 1
-        for (int y0 = r0; y0 < r1; y0 += 4) {
-            if (y0 + 4 < r1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) load_row(min(y0 + 5 + j, h - 1), nxt[j]);
-            }
+        auto four_rows = [&](uint32_t (&below)[4][3]) {                       // rows whose row below is inside the image
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int y = y0 + j;
-                if (y < r1) {                                                 // uniform over the warp
-                    const uint32_t D = (y + 1 < h) ? gray4_of(cur[j][0], cur[j][1], cur[j][2]) : U;     // reflect-101: g[h] = g[h-2]
-                    uint32_t l = __shfl_up_sync(0xffffffffu, C, 1) >> 24, r = __shfl_down_sync(0xffffffffu, C, 1) & 0xffu;
-                    if (at_left) l = (C >> 8) & 0xffu;                        // g[-1] = g[1]
-                    if (at_right) r = (C >> 16) & 0xffu;                      // g[w] = g[w-2]
-                    const uint32_t Lw = __byte_perm(C, l, 0x2104);            // [l, c0, c1, c2]
-                    const uint32_t Rw = __byte_perm(C, r, 0x4321);            // [c1, c2, c3, r]
-                    constexpr uint32_t kA = 0x0001fc01u;                      // [ 1, -4,  1,  0]
-                    constexpr uint32_t kB = 0x01fc0100u;                      // [ 0,  1, -4,  1]
-                    const int L0 = dp4a_us(D, 0x00000001u, dp4a_us(U, 0x00000001u, dp4a_us(Lw, kA, 0)));
-                    const int L1 = dp4a_us(D, 0x00000100u, dp4a_us(U, 0x00000100u, dp4a_us(Lw, kB, 0)));
-                    const int L2 = dp4a_us(D, 0x00010000u, dp4a_us(U, 0x00010000u, dp4a_us(Rw, kA, 0)));
-                    const int L3 = dp4a_us(D, 0x01000000u, dp4a_us(U, 0x01000000u, dp4a_us(Rw, kB, 0)));
-                    if (counts) {
-                        pl += L0 + L1 + L2 + L3;
-                        pl2 += (unsigned)(L0 * L0) + (unsigned)(L1 * L1) + (unsigned)(L2 * L2) + (unsigned)(L3 * L3);
-                    }
-                    U = C;
-                    C = D;
-                }
+                const uint32_t D = gray4_of(below[j][0], below[j][1], below[j][2]);
+                march_row(U, C, D, sel_l, sel_r, pl, pl2);
+                U = C;
+                C = D;
             }
+        };
+        // whole groups first (all four rows inside this warp's range and above the image's last row), two per trip so that
+        // the two row buffers swap roles without register moves
+        int y0 = r0, groups = max(0, min(r1, h - 1) - r0) / 4;
+#pragma unroll 1
+        for (; groups >= 2; groups -= 2, y0 += 8) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { cur[j][0] = nxt[j][0]; cur[j][1] = nxt[j][1]; cur[j][2] = nxt[j][2]; }
+            for (int j = 0; j < 4; ++j) load_row(y0 + 5 + j, gb[j]);
+            four_rows(ga);
+            if (y0 + 8 < r1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_row(y0 + 9 + j, ga[j]);
+            }
+            four_rows(gb);
+        }
+        if (groups) {
+            if (y0 + 4 < r1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_row(y0 + 5 + j, gb[j]);
+            }
+            four_rows(ga);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ga[j][0] = gb[j][0]; ga[j][1] = gb[j][1]; ga[j][2] = gb[j][2]; }
+            y0 += 4;
+        }
+        // what is left (fewer than four rows, or the image's last group): row by row, with the reflect-101 bottom edge
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int y = y0 + j;
+            if (y < r1) {                                                     // uniform over the warp
+                const uint32_t D = (y + 1 < h) ? gray4_of(ga[j][0], ga[j][1], ga[j][2]) : U;        // g[h] = g[h-2]
+                march_row(U, C, D, sel_l, sel_r, pl, pl2);
+                U = C;
+                C = D;
+            }
         }
     }
+    if (!counts) { pl = 0; pl2 = 0u; }
     pl = __reduce_add_sync(0xffffffffu, pl);
     pl2 = __reduce_add_sync(0xffffffffu, pl2);                                // <= 30 lanes x 32 rows x 4 x 1020^2 < 2^32
     if (lane == 0) { red[warp][0] = pl; red[warp][1] = (int)pl2; }
