@@ -248,7 +248,7 @@ tiled_fn pick_tiled(bool scores, bool lanczos, int th, bool col, bool raw)
 // wide boxes {tiled_wide_bw(c) bytes, wide_rows[c]} through a uint32 view; seam boxes over the window tensor (x360_tiled.cuh);
 // store box {96, tile height, 1} of uint8 [F*V][oh][3 ow].  *wide_ok / *seam_ok report what could be encoded.
 bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max, bool with_in, uint8_t *out, int FV, int oh,
-                       int ow, int tile_h, bool with_out, TiledMaps *tm, bool raw, const int *wide_rows, bool *wide_ok, bool *seam_ok)
+                       int ow, int tile_h, bool with_out, TiledMaps *tm, bool raw, bool col_only, const int *wide_rows, bool *wide_ok, bool *seam_ok)
 {
     encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
@@ -265,7 +265,7 @@ bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max,
         for (int k = 0; k < kTNumBox; ++k) {
             const int rows = rows_max - kTBoxRows * (kTNumBoxH - 1 - k / kTNumBoxW);
             const int wk = k % kTNumBoxW;
-            if (!put(&tm->m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, (void *)frames, dims, strides, (cuuint32_t)(raw ? 64 * (std::min(wk, 3) + 1) : 48 * (wk + 1)),
+            if (!put(&tm->m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, (void *)frames, dims, strides, (cuuint32_t)tiled_box_bw(raw, col_only, raw ? std::min(wk, 3) : wk),
                      (cuuint32_t)(rows < 8 ? 8 : rows), CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
                 return false;
         }
@@ -285,7 +285,7 @@ bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max,
             const cuuint64_t st[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * n_rows};
             void *base = (void *)(frames + (size_t)W * 3 - kTSeamHalf);
             for (int w = 0; w < 4 && *seam_ok; ++w)
-                if (!put(&tm->m[kTMapSeam0 + w], CU_TENSOR_MAP_DATA_TYPE_UINT8, base, d1, st, (cuuint32_t)(64 * (w + 1)), (cuuint32_t)(rows_max < 8 ? 8 : rows_max),
+                if (!put(&tm->m[kTMapSeam0 + w], CU_TENSOR_MAP_DATA_TYPE_UINT8, base, d1, st, (cuuint32_t)tiled_box_bw(true, col_only, w), (cuuint32_t)(rows_max < 8 ? 8 : rows_max),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
                     *seam_ok = false;
             for (int c = 0; c < kTNumWide && *seam_ok && *wide_ok; ++c)
@@ -467,9 +467,9 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
         }
         // 16-row tiles pay the per-frame overheads over half the pixels and reuse fewer records (cfg2: 0.89 at equal CTAs/SM)
         const double th_factor = th == 32 ? 1.0 : 0.93;
-        const int unit = raw ? 64 : 48;
-        for (int bw = raw ? 128 : 96; bw <= (raw ? 256 : 48 * kTNumBoxW); bw += unit)
+        for (int wc = 1; wc < (raw ? 4 : kTNumBoxW); ++wc)
             for (int r = 24; r <= 96; r += kTBoxRows) {
+                const int bw = tiled_box_bw(raw, col, wc);
                 const size_t smem = tiled_smem_bytes(r, bw, scores, lanczos, th, col, raw) + 1024;
                 if (smem > (size_t)kTiledSmemCap) continue;
                 int occ = (int)((227 * 1024) / smem);
@@ -478,7 +478,7 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
                 wide_class_rows(r, bw, wr);
                 size_t fit = 0, fit_wide = 0;
                 for (const Foot &ft : feet) {
-                    if (ft.rows <= r && (ft.need + unit - 1) / unit * unit <= bw) { ++fit; continue; }
+                    if (ft.rows <= r && tiled_box_bw(raw, col, std::max(0, tiled_box_class(raw, col, ft.need))) <= bw) { ++fit; continue; }
                     if (opts.no_wide) continue;
                     for (int c = 0; c < kTNumWide; ++c)
                         if (ft.need <= tiled_wide_bw(c) && ft.rows <= wr[c]) { ++fit_wide; break; }
@@ -634,7 +634,7 @@ static const MapCache *tiled_maps(x360_plan *pl, const TiledGroup &G, MapCache &
     memset(&mc.tms, 0, sizeof mc.tms);
     if ((mc.stage_ok || mc.store_ok) &&
         !encode_tiled_maps(frames, n_frames, g.H, g.W, t_rows, mc.stage_ok != 0, out_views, n_frames * pl->p.n_views, g.oh, g.ow, t_th, mc.store_ok != 0,
-                           &mc.tms, G.t_raw[sc], wide_rows, &mc.wide_ok, &mc.seam_ok)) {
+                           &mc.tms, G.t_raw[sc], G.col_u0, wide_rows, &mc.wide_ok, &mc.seam_ok)) {
         mc.stage_ok = 0;                               // every tile goes direct, byte stores
         mc.store_ok = 0;
         mc.wide_ok = mc.seam_ok = false;
@@ -980,8 +980,8 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
                 G.t_raw[sc] = raw;
                 const bool lab_cap = !(lab_int("X360_TILED_GENERAL_ONLY", 0) && G.col_u0);
                 if (const char *e = lab_cap ? lab_env("X360_TILED_BW") : nullptr) {
-                    const int v = atoi(e), unit = raw ? 64 : 48;
-                    bw = (v >= unit && v <= (raw ? 256 : 48 * kTNumBoxW) && v % unit == 0) ? v : bw;
+                    for (int wc = 0; wc < (raw ? 4 : kTNumBoxW); ++wc)
+                        if (tiled_box_bw(raw, G.col_u0, wc) == atoi(e)) bw = atoi(e);
                 }
                 if (const char *e = lab_cap ? lab_env("X360_TILED_ROWS") : nullptr) rows = round_up(atoi(e) < 24 ? 24 : atoi(e), kTBoxRows);
                 while (rows > 24 && tiled_smem_bytes(rows, bw, sc != 0, lz, th, G.col_u0, raw) > (size_t)kTiledSmemCap) rows -= kTBoxRows;
@@ -1001,7 +1001,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
                 // survey finds enough of them to fill that launch's grid several times over: measured neutral on cfg4 (~5000
                 // pairs, direct share 12 % -> 2 %), 10 % slower on cfg1 (~1100 pairs: two half-empty waves), so small jobs keep
                 // the direct gathers for those tiles.
-                const int rows2 = lab_int("X360_T2_ROWS", 64), bw2 = lab_int("X360_T2_BW", raw ? 256 : 240);
+                const int rows2 = lab_int("X360_T2_ROWS", 64), bw2 = lab_int("X360_T2_BW", raw ? tiled_box_bw(true, G.col_u0, 3) : 240);
                 if (!lz && !(raw && G.col_u0) && !pl->opts.no_wide && rows2 * bw2 > rows * bw && !lab_int("X360_ONE_LAUNCH", 0)) {
                     G.t2_rows[sc] = rows2;
                     G.t2_bw[sc] = bw2;

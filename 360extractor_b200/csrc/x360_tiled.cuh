@@ -60,6 +60,20 @@ constexpr int kTBoxRows = 8;          // granularity of the footprint row capaci
 constexpr int kTNumBoxW = 5;          // load box widths 48, 96, 144, 192, 240 bytes (16, 32, ... source pixels)
 constexpr int kTNumBoxH = 3;          // load box heights rows_max - 16, rows_max - 8, rows_max
 constexpr int kTNumBox = kTNumBoxW * kTNumBoxH;
+// Width (= shared-memory row pitch) of regular box class w.  Planes: 48 (w + 1).  Raw gather, column-only views: 64 (w + 1) —
+// a warp's 32 lanes read one source row, any pitch does.  Raw gather, general views (pole faces, inclined views): 64 (w + 1) - 16
+// = 48, 112, 176, 240: a warp's lanes follow a line of any slope through the footprint, and with a pitch of 128 or 256 bytes
+// every source row starts in bank 0 (ncu, cfg4's pole faces: 57 % of the shared-memory wavefronts were bank-conflict replays).
+// A TMA box is a multiple of 16 bytes wide, so pitch / 4 mod 32 cannot be odd; = 4 mod 8 is the best there is (rows r, r + 8
+// alias).  w < 4 for the raw gather.
+#ifndef X360_RAW_SKEW
+#define X360_RAW_SKEW 16
+#endif
+__host__ __device__ constexpr int tiled_box_bw(bool raw, bool col_only, int w) { return raw ? 64 * (w + 1) - (col_only ? 0 : X360_RAW_SKEW) : 48 * (w + 1); }
+__host__ __device__ constexpr int tiled_box_class(bool raw, bool col_only, int need)       // smallest class that holds `need` bytes per row
+{
+    return raw ? (need + (col_only ? 0 : X360_RAW_SKEW) + 63) / 64 - 1 : (need + 47) / 48 - 1;
+}
 constexpr int kTMaxUnitViews = 8;     // views sharing one map evaluation
 #ifndef X360_RAW_NB
 #define X360_RAW_NB 3
@@ -701,10 +715,10 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             const int e_a = delta + 3 * (g.W - x_org);                   // seam: where a box row passes column W-1 of its source row
             // box class: a regular box {64 / 48 (wsel + 1) bytes x one of three heights}, else a wide class (kTNumWide)
             int tmi = -1;
-            uint32_t bw = RAW ? 64u : 48u, box_rows = 8u;
+            uint32_t bw = (uint32_t)tiled_box_bw(RAW, COLSEL, 0), box_rows = 8u;
             {
-                const int wsel = RAW ? (need + 63) / 64 - 1 : (need + 47) / 48 - 1;
-                const uint32_t bwr = (RAW ? 64u : 48u) * (uint32_t)(wsel + 1);
+                const int wsel = max(0, tiled_box_class(RAW, COLSEL, need));
+                const uint32_t bwr = (uint32_t)tiled_box_bw(RAW, COLSEL, wsel);
                 if (rows <= a.rows_max && bwr <= (uint32_t)a.bw_max) {
                     // one TMA box per frame: the smallest of the three box heights that covers the footprint (seam: the full height)
                     const int hsel = seam ? kTNumBoxH - 1 : max(0, kTNumBoxH - 1 - (a.rows_max - rows) / kTBoxRows);
