@@ -91,6 +91,7 @@ SYMBOLS = {
     "x360_launch_count": (_i64, []),
     "x360_plan_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(_i32)] * 4),
     "x360_plan_tile_modes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint32)]),
+    "x360_plan_transposed_blocks": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64)]),
 }
 
 _lib = None

@@ -303,6 +303,10 @@ bool encode_tiled_maps(const uint8_t *frames, int F, int H, int W, int rows_max,
         const cuuint64_t strides[2] = {(cuuint64_t)ow * 3, (cuuint64_t)ow * 3 * oh};
         if (!put(&tm->m[kTMapOut], CU_TENSOR_MAP_DATA_TYPE_UINT8, (void *)out, dims, strides, (cuuint32_t)(kTile * 3), (cuuint32_t)tile_h, CU_TENSOR_MAP_L2_PROMOTION_NONE))
             return false;
+        // transposed tiles of the 16-row variant: tile_h pixels wide, kTile rows
+        if (tile_h == 16 && oh >= kTile &&
+            !put(&tm->m[kTMapOutT], CU_TENSOR_MAP_DATA_TYPE_UINT8, (void *)out, dims, strides, (cuuint32_t)(tile_h * 3), (cuuint32_t)kTile, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+            return false;
     }
     return true;
 }
@@ -392,6 +396,22 @@ HostUnits build_units(const double *R, int V, int W, const Geom &g, bool share, 
     return h;
 }
 
+// 1 / D when every multi-view unit's shifts are 0, D, 2D, ... (source pixels) with one D for all of them and n D <= W; else 0.
+double even_yaw_spacing(const HostUnits &h, int W)
+{
+    double D = 0.0;
+    for (const TiledUnit &t : h.units) {
+        if (t.n < 2) continue;
+        const double d = h.shift[(size_t)t.first + 1];
+        if (d <= 0.0 || (D > 0.0 && std::fabs(d - D) > 1e-6 * W)) return 0.0;
+        D = d;
+        if (t.n * d > (double)W * (1.0 + 1e-9)) return 0.0;
+        for (int i = 0; i < t.n; ++i)
+            if (std::fabs(h.shift[(size_t)t.first + i] - i * d) > 1e-6 * W) return 0.0;
+    }
+    return D > 0.0 ? 1.0 / D : 0.0;
+}
+
 // Host estimate of the per-tile source footprints (9 sample points of each tile, + the 1-px halo the fused
 // score gathers when `scores`) -> the tile
 // height (32 or 16 output rows) and staging capacity (footprint rows, raw bytes per row) that maximise
@@ -411,6 +431,23 @@ bool column_only_map_x(const double *R, int V)
     return V > 0;
 }
 
+// Transposed tiles (x360_tiled.cuh, TiledArgs::tr_tab): which plans may have them, and which 32 x 32 output blocks take them.
+bool transposable_plan(const Geom &g, bool col_only, bool raw, bool scores, bool lanczos)
+{
+    return raw && !col_only && !scores && !lanczos && g.ow == g.oh && g.ow % kTile == 0 && !lab_int("X360_NO_TR", 0);
+}
+// the source ROW moves faster along output x than along output y at the block's centre: lanes along x would read a steep line
+bool block_transposed(const Geom &g, const double *Rv, int bx, int by)
+{
+    auto src_row = [&](double x, double y) {
+        const double xn = (x - g.cx) / g.f, yn = (y - g.cy) / g.f;
+        const double v0 = xn * Rv[0] + yn * Rv[1] + Rv[2], v1 = xn * Rv[3] + yn * Rv[4] + Rv[5], v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
+        return (std::asin(v1 / std::sqrt(v0 * v0 + v1 * v1 + v2 * v2)) / 3.14159265358979323846 + 0.5) * g.H;
+    };
+    const double xc = bx * kTile + 0.5 * (kTile - 1), yc = by * kTile + 0.5 * (kTile - 1), d = 8.0;
+    return std::fabs(src_row(xc + d, yc) - src_row(xc - d, yc)) > std::fabs(src_row(xc, yc + d) - src_row(xc, yc - d));
+}
+
 void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool scores, const PlanOpts &opts, int *rows_out, int *bw_out, int *tile_h_out,
                      long long *unfit_out = nullptr)
 {
@@ -422,6 +459,7 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
     int best_rows = 40, best_bw = 144, best_th = 32;
     const int m = lanczos ? 7 : 0;                                        // 8x8 taps: 3 before, 4 after
     const bool raw = tiled_raw(scores, lanczos, opts);
+    const bool can_tr = transposable_plan(g, col, raw, scores, lanczos);
     struct Foot { int rows, need; bool seam; };
     for (int th = 32; th >= 16; th -= 16) {
         if (opts.force_th && opts.force_th != th) continue;
@@ -433,12 +471,15 @@ void choose_capacity(const Geom &g, const double *R, int V, bool lanczos, bool s
             for (int ty = 0; ty < tiles_y; ++ty)
                 for (int tx = 0; tx < g.tiles_x; ++tx) {
                     ++total;
+                    // the tile's rectangle of the view: 32 x th at (32 tx, th ty), or — a transposed block — th x 32
+                    int rx = tx * kTile, ry = ty * th, rw = kTile, rh = th;
+                    if (th == 16 && can_tr && block_transposed(g, Rv, tx, ty >> 1)) { rx = tx * kTile + (ty & 1) * th; ry = (ty >> 1) * kTile; rw = th; rh = kTile; }
                     int xs[9], ymin = INT_MAX, ymax = INT_MIN;
                     for (int j = 0; j < 3; ++j)
                         for (int i = 0; i < 3; ++i) {
                             const int hl = scores ? 1 : 0;                        // halo
-                            const double x = std::min<double>(std::max(0, tx * kTile - hl + i * (kTile - 1 + 2 * hl) / 2), g.ow - 1);
-                            const double y = std::min<double>(std::max(0, ty * th - hl + j * (th - 1 + 2 * hl) / 2), g.oh - 1);
+                            const double x = std::min<double>(std::max(0, rx - hl + i * (rw - 1 + 2 * hl) / 2), g.ow - 1);
+                            const double y = std::min<double>(std::max(0, ry - hl + j * (rh - 1 + 2 * hl) / 2), g.oh - 1);
                             const double xn = (x - g.cx) / g.f, yn = (y - g.cy) / g.f;
                             const double v0 = xn * Rv[0] + yn * Rv[1] + Rv[2], v1 = xn * Rv[3] + yn * Rv[4] + Rv[5],
                                          v2 = xn * Rv[6] + yn * Rv[7] + Rv[8];
@@ -537,6 +578,9 @@ struct TiledGroup {
     TiledUnit *d_units[4] = {};
     int *d_unit_view[4] = {};
     double *d_unit_shift[4] = {};
+    uint8_t *d_tr_tab = nullptr;         // TiledArgs::tr_tab: [plan views][32 x 32 blocks], or nullptr
+    long long n_tr_blocks = 0;
+    double rot_inv_pitch[4] = {0, 0, 0, 0};   // TiledArgs::rot_inv_pitch of each level (0: views not evenly spaced, or a general group)
 };
 
 struct x360_plan {
@@ -704,6 +748,8 @@ static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch,
     a.unit_view = G.d_unit_view[level];
     a.unit_shift = G.d_unit_shift[level];
     a.n_units = n_units;
+    a.rot_inv_pitch = lab_int("X360_NO_ROT", 0) ? 0.0 : G.rot_inv_pitch[level];
+    a.tr_tab = (!scores && t_th == 16 && G.t_raw[sc]) ? G.d_tr_tab : nullptr;
     int FG = (n_frames + n_chunks - 1) / n_chunks;
     if (const char *e = lab_env("X360_FG")) FG = atoi(e) > 0 ? atoi(e) : FG;
     if (FG > n_frames) FG = n_frames;
@@ -1060,10 +1106,26 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
                 if (pl->view_group[(size_t)v] == gi) ids.push_back(v);
             std::vector<double> Rg(ids.size() * 9);
             for (size_t i = 0; i < ids.size(); ++i) memcpy(&Rg[i * 9], params->R + 9 * ids[i], 9 * sizeof(double));
+            // transposed-tile table of the group's views (TiledArgs::tr_tab), where the no-score launch can take them
+            if (G.t_th[0] == 16 && transposable_plan(pl->g, G.col_u0, G.t_raw[0], false, params->interp == X360_INTERP_LANCZOS4)) {
+                const int bxn = pl->g.tiles_x, byn = pl->g.oh / kTile;
+                std::vector<uint8_t> tab((size_t)params->n_views * bxn * byn, 0);
+                size_t n_tr = 0;
+                for (int v : ids)
+                    for (int by = 0; by < byn; ++by)
+                        for (int bx = 0; bx < bxn; ++bx)
+                            n_tr += (tab[((size_t)v * byn + by) * bxn + bx] = block_transposed(pl->g, params->R + 9 * v, bx, by) ? 1 : 0);
+                if (n_tr) {
+                    G.n_tr_blocks = (long long)n_tr;
+                    e = cudaMalloc(&G.d_tr_tab, tab.size());
+                    if (e == cudaSuccess) e = cudaMemcpy(G.d_tr_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice);
+                }
+            }
             for (int lv = 0; lv < 4 && e == cudaSuccess; ++lv) {
                 HostUnits h = build_units(Rg.data(), (int)ids.size(), params->src_w, pl->g, share, kTMaxUnitViews >> lv);
                 for (int &v : h.view) v = ids[(size_t)v];                       // group-local -> plan view index
                 G.n_units[lv] = (int)h.units.size();
+                G.rot_inv_pitch[lv] = G.col_u0 ? even_yaw_spacing(h, params->src_w) : 0.0;
                 e = cudaMalloc(&G.d_units[lv], sizeof(TiledUnit) * h.units.size());
                 if (e == cudaSuccess) e = cudaMalloc(&G.d_unit_view[lv], sizeof(int) * h.view.size());
                 if (e == cudaSuccess) e = cudaMalloc(&G.d_unit_shift[lv], sizeof(double) * h.shift.size());
@@ -1113,6 +1175,7 @@ int x360_plan_destroy(x360_plan *pl)
             cudaFree(pl->grp[gi].d_unit_view[lv]);
             cudaFree(pl->grp[gi].d_unit_shift[lv]);
         }
+    for (int gi = 0; gi < 2; ++gi) cudaFree(pl->grp[gi].d_tr_tab);
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_frames[i]);
         cudaFree(pl->d_views[i]);
@@ -1164,6 +1227,14 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->grp[0].t_th[0]) : kThreads;
     if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->grp[0].t_smem[0]
                                   : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
+    return X360_OK;
+}
+
+int x360_plan_transposed_blocks(const x360_plan *pl, int64_t *n_blocks)
+{
+    if (!pl || !n_blocks) return fail(X360_E_INVALID, "null argument");
+    *n_blocks = 0;
+    for (int gi = 0; gi < pl->n_groups; ++gi) *n_blocks += pl->grp[gi].n_tr_blocks;
     return X360_OK;
 }
 

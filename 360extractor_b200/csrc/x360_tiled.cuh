@@ -100,13 +100,14 @@ __host__ __device__ constexpr int tiled_wide_bw(int c) { return 384 + 192 * c; }
 // y+1's head side by side.  Regular widths 64 k (k <= 4) at the full box height, then the wide classes.
 constexpr int kTSeamHalf = 1024;
 constexpr int kTNumSeam = 4 + kTNumWide;
-constexpr int kTMapWide0 = kTNumBox, kTMapSeam0 = kTMapWide0 + kTNumWide, kTMapOut = kTMapSeam0 + kTNumSeam, kTNumMaps = kTMapOut + 1;
+constexpr int kTMapWide0 = kTNumBox, kTMapSeam0 = kTMapWide0 + kTNumWide, kTMapOut = kTMapSeam0 + kTNumSeam, kTMapOutT = kTMapOut + 1, kTNumMaps = kTMapOutT + 1;
 
 struct TiledMaps {
     // [0, 15)  uint8 [F][H][3W], box {48 (w + 1), rows_max - 8 (2 - h), 1} at [h * 5 + w]; raw gather: {64 (w + 1), ..}, w < 4
     // [15, 19) wide: uint32 [F][H][3W/4], box {tiled_wide_bw(c) / 4, wide_rows[c], 1}
     // [19, 27) seam: window tensor [1][F H - 1][2 kTSeamHalf] (uint8: widths 64 (w + 1) x rows_max; uint32: the wide classes)
     // [27]     out: uint8 [F*V][oh][3 ow], box {96, tile height, 1}
+    // [28]     out, transposed tiles (16-row variant): box {48, 32, 1}
     CUtensorMap m[kTNumMaps];
 };
 
@@ -144,6 +145,17 @@ struct TiledArgs {
     // mode 0: one launch, such tiles go straight to the direct gathers.
     int mode, defer_cap, defer_sub;
     unsigned *defer_list, *defer_count;
+    // Column-only units whose views are spaced by a constant yaw (a ring): 1 / (that spacing in source pixels), else 0.  A tile
+    // then starts its walk over the unit's views at the view for which its footprint lies in source sector k = 0, 1, ... in
+    // step with every other tile: overlapping views read the same source bytes at the same time (L2 hits instead of a
+    // second trip to DRAM).
+    double rot_inv_pitch;
+    // Transposed tiles (raw gather of general views, 16-row tiles, square views of whole 32 x 32 blocks): tr_tab[view][block] != 0
+    // -> the two tiles of that 32 x 32 output block are its left and right halves (16 wide, 32 tall) instead of its upper and
+    // lower ones, and the lanes run down the block's rows.  Set where the source row changes faster along output x than along
+    // output y (the left / right quadrants of a pole face): there a warp's lanes would read a near-vertical line of the
+    // footprint (bank conflicts) and the walk down a column would never reuse a record.  Same arithmetic per pixel.
+    const uint8_t *tr_tab;
     int wide_rows[kTNumWide];         // box height of each wide class (raw buffer bytes / class width, at most 256)
 };
 
@@ -593,7 +605,15 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
         if (only_vi >= 0) { unit.first += only_vi; unit.n = 1; }   // second launch: the one deferred view, as a unit of its own
         const int chunk = local / tiles_per_view, tile = local - chunk * tiles_per_view;
         const int ty = tile / g.tiles_x;
-        const int x0 = (tile - ty * g.tiles_x) * kTile, y0 = ty * TH;
+        int x0 = (tile - ty * g.tiles_x) * kTile, y0 = ty * TH;
+        // transposed tile: from here on (x0, y0), the lane and the row index k are coordinates of the TRANSPOSED view — lane along
+        // the real y axis, rows along the real x axis; only the map's arguments and the store know
+        constexpr bool TRANSPOSABLE = RAW && !COLSEL && !SCORES && TP == 4;
+        bool tr = false;
+        if constexpr (TRANSPOSABLE) {
+            if (a.tr_tab) tr = a.tr_tab[(size_t)a.unit_view[a.units[u].first] * ((size_t)g.tiles_x * (a.tiles_y >> 1)) + (size_t)(ty >> 1) * g.tiles_x + x0 / kTile] != 0;
+            if (tr) { const int bx = x0; x0 = (ty >> 1) * kTile; y0 = bx + (ty & 1) * TH; }
+        }
         int f_begin = chunk * a.FG, f_end = min(a.F, f_begin + a.FG);
         if (DEFER && a.mode == 2) {                            // this item's share of the chunk's frames
             const int len = (f_end - f_begin + a.defer_sub - 1) / a.defer_sub;
@@ -604,15 +624,16 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
         const bool full = (x0 + kTile <= g.ow) && (y0 + TH <= g.oh);
 
         // ---- 1. the unit's map for this tile, to shared memory: fp64 map_x, Q5 map_y -------------
-        double hu0 = 0.0;
+        double hu0 = 0.0, u_first = 0.0;
         int hsy = 0;
         bool hvalid = false;
         {
             const double *R = a.R + 9 * a.unit_view[unit.first];
             const int x = min(x0 + lane, g.ow - 1);
-            const double xn = map_xn(g, x);
+            const double xn = tr ? map_yn(g, x) : map_xn(g, x);          // transposed: the lane's coordinate is the real y
             // yn of this warp's rows: lane k divides for row k, the loop broadcasts (a division per pixel otherwise)
-            const double yn_lane = map_yn(g, min(y0 + warp * kTP + min(lane, kTP - 1), g.oh - 1));
+            const int yrow = min(y0 + warp * kTP + min(lane, kTP - 1), g.oh - 1);
+            const double yn_lane = tr ? map_xn(g, yrow) : map_yn(g, yrow);
             double rxz = 0.0;
             int sy_hi = 0;
             // (Lanczos4 plans are typically single-frame jobs — nothing amortises the map — and run 12 warps per SM: two pixels
@@ -621,11 +642,13 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
 #pragma unroll kMapUnroll
             for (int k = 0; k < kTP; ++k) {
                 double v0, v1, v2;
-                map_ray_n(R, xn, __shfl_sync(0xffffffffu, yn_lane, k), v0, v1, v2);
+                const double yn_k = __shfl_sync(0xffffffffu, yn_lane, k);
+                if (TRANSPOSABLE && tr) map_ray_n(R, yn_k, xn, v0, v1, v2);           // (real xn, real yn): the same expression, bit for bit
+                else map_ray_n(R, xn, yn_k, v0, v1, v2);
                 // yaw-only rotations: v0 and v2 — hence map_x and the ray's horizontal length — do not depend on the row:
                 // one atan2 and one square root per column and warp
                 if (!col_u0) { u0s[k * kTT + tid] = map_u_of(g, v0, v2); rxz = map_rxz(v0, v2); }
-                else if (k == 0) { u0s[lane] = map_u_of(g, v0, v2); rxz = map_rxz(v0, v2); }
+                else if (k == 0) { u_first = map_u_of(g, v0, v2); u0s[lane] = u_first; rxz = map_rxz(v0, v2); }
                 const int syq = q5_of(map_y_from(g, v1, rxz));             // 0 .. 32 H < 2^20
                 sy_s[k * kTT + tid] = (uint8_t)syq;
                 sy_s[TH * kTile + k * kTT + tid] = (uint8_t)(syq >> 8);
@@ -643,7 +666,10 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
             }
         }
 
-        for (int vi = 0; vi < unit.n; ++vi) {
+        int rot = 0;                                             // uniform: every warp holds the same column values
+        if (col_u0 && a.rot_inv_pitch > 0.0 && unit.n > 1) rot = (int)(__shfl_sync(0xffffffffu, u_first, kTile / 2) * a.rot_inv_pitch) % unit.n;
+        for (int vk = 0; vk < unit.n; ++vk) {
+            const int vi = vk >= rot ? vk - rot : vk - rot + unit.n;
             const int v = a.unit_view[unit.first + vi];
             const double shift = (DEFER && a.mode == 2) ? 0.0 : a.unit_shift[unit.first + vi];   // second launch: the view's own map (unit of one)
 
@@ -956,8 +982,19 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                   if constexpr (RAW) {
                     uint2 X = make_uint2(0u, 0u), Y = make_uint2(0u, 0u), X2 = make_uint2(0u, 0u), Y2 = make_uint2(0u, 0u);
                     const uint32_t up = rb * raw_bytes, lw = up + bw;        // this frame's buffer: upper / lower record of pixel k at pa[k] + up / + lw
+                    uint32_t tp1 = 0u, tp2 = 0u;                              // transposed tiles: pixels 1 and 2 of this thread's four
                     auto emit = [&](int k, const uint2 &U, const uint2 &V) {
                         const uint32_t pxl = combine_pairs(U, V, pb[k], pc[k]);
+                        if constexpr (TRANSPOSABLE) {
+                            if (tr) {                                         // uniform.  The thread's pixels are 12 consecutive bytes of tile row `lane` (rows of 48)
+                                const uint32_t tw = ot - my_word + (uint32_t)(lane * (TH * 3) + warp * (kTP * 3));
+                                if (k == 1) tp1 = pxl;                        // (walk order: 1, 2, 0, 3)
+                                if (k == 2) { tp2 = pxl; asm volatile("st.shared.u32 [%0], %1;" ::"r"(tw + 4u), "r"(__byte_perm(tp1, pxl, 0x5421)) : "memory"); }
+                                if (k == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tw), "r"(__byte_perm(pxl, tp1, 0x4210)) : "memory");
+                                if (k == 3) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tw + 8u), "r"(__byte_perm(tp2, pxl, 0x6542)) : "memory");
+                                return;
+                            }
+                        }
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ot + (uint32_t)(k * kTile * 3)), "r"(__byte_perm(pxl, nb, pack_sel)) : "memory");
                         if (SCORES) gt.g[warp * kTP + k + 1][lane] = (uint8_t)gray_of(pxl);
@@ -1054,8 +1091,20 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                             return generic ? LinearSampler::gather_generic(fb, d, g, nullptr) : LinearSampler::gather_fast(fb, d, g, nullptr);
                         }
                     };
+                    bool plain = true;
+                    if constexpr (TRANSPOSABLE) {
+                        if (tr) {                                             // (see emit above)
+                            uint32_t *const trow = reinterpret_cast<uint32_t *>(dsm + tile_off + (uint32_t)(lane * (TH * 3) + warp * (kTP * 3)));
+                            const uint32_t p0 = direct(0), p1 = direct(1), p2 = direct(2), p3 = direct(3);
+                            trow[0] = __byte_perm(p0, p1, 0x4210);
+                            trow[1] = __byte_perm(p1, p2, 0x5421);
+                            trow[2] = __byte_perm(p2, p3, 0x6542);
+                            plain = false;
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < kTP; ++k) {
+                        if (!plain) break;
                         const uint32_t pxl = direct(k);
                         const uint32_t nb = __shfl_down_sync(0xffffffffu, pxl, 1);
                         if (q != 3) orow[k * (kTile * 3 / 4)] = __byte_perm(pxl, nb, pack_sel);
@@ -1074,15 +1123,23 @@ extract_tiled(const __grid_constant__ TiledArgs a, const __grid_constant__ Tiled
                 if (a.store_ok) {
                     if (tid == 0) {
                         if (RAW && staged && f + NB < f_end) issue_box(f + NB, rb);
-                        tma_store_tile(&tms.m[kTMapOut], RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
+                        if (TRANSPOSABLE && tr) tma_store_tile(&tms.m[kTMapOutT], dsm_s + tile_off, y0 * 3, x0, f * a.V + v);   // real (x, y) = (y0, x0)
+                        else tma_store_tile(&tms.m[kTMapOut], RAW ? dsm_s + tile_off : otile_s, x0 * 3, y0, f * a.V + v);
                     }
                 } else {
                     if (RAW && staged && f + NB < f_end && tid == 0) issue_box(f + NB, rb);
-                    const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(TH, g.oh - y0);
                     uint8_t *out_view = a.out + ((size_t)f * a.V + v) * view_bytes;
+                    if (TRANSPOSABLE && tr) {                                 // whole blocks only: kTile rows of TH pixels at real (y0, x0)
+                        for (int i = tid; i < TH * kTile * 3; i += kTT) {
+                            const int row = i / (TH * 3), bb = i - row * (TH * 3);
+                            out_view[(size_t)(x0 + row) * opitch + (size_t)y0 * 3 + bb] = dsm[tile_off + i];
+                        }
+                    } else {
+                    const int wbytes = min(kTile, g.ow - x0) * 3, hrows = min(TH, g.oh - y0);
                     for (int i = tid; i < TH * kTile * 3; i += kTT) {
                         const int row = i / (kTile * 3), bb = i - row * (kTile * 3);
                         if (row < hrows && bb < wbytes) out_view[(size_t)(y0 + row) * opitch + (size_t)x0 * 3 + bb] = dsm[tile_off + i];
+                    }
                     }
                 }
                 if (SCORES) {

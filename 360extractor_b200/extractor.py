@@ -149,6 +149,13 @@ class Extractor:
         return {"staged": int(out[0]), "direct_aligned": int(out[1]), "direct_bytewise": int(out[2]),
                 "staged_wide": int(out[3]), "staged_seam": int(out[4])}
 
+    def transposed_blocks(self):
+        """32 x 32 output blocks (over all views) the plan gathers with the lanes running down the rows (pole-face quadrants
+        where the source row changes faster along x than along y); a layout choice, the pixels are the same."""
+        n = ctypes.c_int64()
+        check(lib().x360_plan_transposed_blocks(self._plan, ctypes.byref(n)))
+        return int(n.value)
+
     # -- the hot path --------------------------------------------------------------------------
     def _host_frames(self, frames):
         frames = np.asarray(frames)

@@ -295,6 +295,10 @@ int x360_plan_info(const x360_plan *plan, int32_t *path, int32_t *grid, int32_t 
  * [1] direct aligned-word gather, [2] direct byte-wise gather (pole rows / odd geometry), [3] staged by a wide box
  * (footprints near the poles), [4] staged across the +-pi seam.  Synchronises the device. */
 int x360_plan_tile_modes(x360_plan *plan, uint32_t *out5);
+/* 32 x 32 output blocks (summed over the views) whose two 16-row tiles the plan processes TRANSPOSED — lanes down the block's
+ * rows, because there the source row changes faster along output x than along y (the left / right quadrants of a pole face):
+ * a layout choice of the gather, the pixels are the same.  0 for plans without such blocks. */
+int x360_plan_transposed_blocks(const x360_plan *plan, int64_t *n_blocks);
 
 #ifdef __cplusplus
 }

@@ -470,6 +470,34 @@ def test_wide_seam_and_second_launch_against_oracle(x360, oracle, cfg, scores):
         assert auto["staged_seam"] > 0, auto
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(512, 1024, 192, 90, "cube", 6, 0, 3), (640, 1280, 160, 90, "cube", 6, -30, 2), (720, 1440, 224, 90, "ring", 5, 70, 2),
+                                 (1024, 2048, 512, 90, "cube", 6, 0, 2), (512, 1024, 96, 120, "cube", 6, 0, 1)])
+def test_transposed_tiles_against_oracle(x360, oracle, cfg):
+    """Square views of whole 32 x 32 blocks with 16-row tiles: the blocks of a general view where the source row changes faster
+    along x than along y are gathered transposed (lanes down the rows).  Same bytes as the oracle, as the 32-row plan (which has
+    no such tiles), with TMA stores and without (odd output pointer)."""
+    H, W, d, fov, layout, n, pitch, F = cfg
+    frames = np.stack([noise_frame(1300 + i, H, W) for i in range(F)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout))
+    want, _, _ = oracle.extract(frames, R, d, fov, 0, want_scores=False)
+    with x360.Extractor(H, W, d, fov, R, "linear", max_batch=F, flags=x360.FLAG_TILE_H16) as ex:
+        assert ex.transposed_blocks() > 0, cfg
+        assert_same(ex.extract(frames, want_scores=False)[0], want, f"{cfg} 16-row tiles, transposed blocks")
+        got, s, s2 = ex.extract_sums(frames)                       # the score variants never transpose: same views all the same
+        assert_same(got, want, f"{cfg} with the split score")
+        import torch
+        dev_frames = torch.from_numpy(frames).cuda()
+        spare = torch.empty(F * len(R) * d * d * 3 + 1, dtype=torch.uint8, device="cuda")
+        views = spare[1:].view(F, len(R), d, d, 3)                  # misaligned output: byte stores instead of TMA stores
+        ex.extract_device(dev_frames, views)
+        torch.cuda.synchronize()
+        assert_same(views.cpu().numpy(), want, f"{cfg} transposed blocks, byte stores")
+    with x360.Extractor(H, W, d, fov, R, "linear", max_batch=F, flags=x360.FLAG_TILE_H32) as ex:
+        assert ex.transposed_blocks() == 0
+        assert_same(ex.extract(frames, want_scores=False)[0], want, f"{cfg} 32-row tiles")
+
+
 def test_two_live_plans_do_not_break_each_other(x360, oracle):
     """The dynamic shared-memory limit belongs to the kernel function: a second, smaller plan must not lower it under a live
     larger one (BlurAnalyzer / create_rectilinear_map build temporary plans while a session is alive)."""
