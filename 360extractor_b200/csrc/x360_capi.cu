@@ -752,6 +752,7 @@ static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch,
     a.tr_tab = (!scores && t_th == 16 && G.t_raw[sc]) ? G.d_tr_tab : nullptr;
     int FG = (n_frames + n_chunks - 1) / n_chunks;
     if (const char *e = lab_env("X360_FG")) FG = atoi(e) > 0 ? atoi(e) : FG;
+    if (const char *e = G.col_u0 ? nullptr : lab_env("X360_FG_GENERAL")) FG = atoi(e) > 0 ? atoi(e) : FG;
     if (FG > n_frames) FG = n_frames;
     a.FG = FG;
     a.n_chunks = (n_frames + FG - 1) / FG;
