@@ -1630,19 +1630,19 @@ static int jpeg_launch(x360_jpeg *e, const uint8_t *images, int n, uint8_t *out,
 {
     const JpegGeom &g = e->g;
     CU(cudaMemsetAsync(e->d_overflow, 0, sizeof(int), st));
-    jpeg_blocks_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n), 128, 0, st>>>(images, g, e->tab, e->d_coef);
-    jpeg_dummy_dc_kernel<<<dim3((unsigned)((g.n_mcu + 127) / 128), (unsigned)n), 128, 0, st>>>(g, e->d_coef);
+    jpeg_blocks_kernel<<<dim3((unsigned)((g.mw + kJbMcus - 1) / kJbMcus), (unsigned)g.mh, (unsigned)n), kJbThreads, 0, st>>>(images, g, e->tab, e->d_coef);
+    if (g.w % 16 || g.h % 16) jpeg_dummy_dc_kernel<<<dim3((unsigned)((g.n_mcu + 127) / 128), (unsigned)n), 128, 0, st>>>(g, e->d_coef);
     jpeg_bits_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n), 128, 0, st>>>(e->d_coef, g, e->d_bits);
     jpeg_scan_kernel<<<(unsigned)n, 1024, 0, st>>>(e->d_bits, g.n_blocks, e->d_view_bits);
     jpeg_bases_kernel<<<1, 32, 0, st>>>(e->d_view_bits, n, e->d_word_base, e->cap_words, e->d_overflow);
-    CU(cudaMemsetAsync(e->d_stream, 0, sizeof(uint32_t) * (size_t)e->cap_words, st));
+    jpeg_zero_kernel<<<148 * 4, 256, 0, st>>>(e->d_stream, e->d_word_base, n, e->d_overflow);
     jpeg_emit_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n), 128, 0, st>>>(e->d_coef, g, e->d_bits, e->d_word_base, e->d_stream, e->d_overflow);
-    jpeg_ffscan_kernel<<<(unsigned)n, 1024, 0, st>>>(e->d_stream, e->d_word_base, e->d_view_bits, e->d_segff, e->max_segs, (int)e->header.size(),
-                                                       e->d_file_bytes, e->d_overflow);
+    jpeg_ffcount_kernel<<<dim3((unsigned)e->max_segs, (unsigned)n), 256, 0, st>>>(e->d_stream, e->d_word_base, e->d_view_bits, e->d_segff, e->max_segs, e->d_overflow);
+    jpeg_ffscan_kernel<<<(unsigned)n, 256, 0, st>>>(e->d_view_bits, e->d_segff, e->max_segs, (int)e->header.size(), e->d_file_bytes, e->d_overflow);
     jpeg_offsets_kernel<<<1, 32, 0, st>>>(e->d_file_bytes, n, offsets, out_capacity, e->d_overflow);
-    jpeg_pack_kernel<<<dim3((unsigned)((e->max_segs + 1 + 127) / 128), (unsigned)n), 128, 0, st>>>(e->d_stream, e->d_word_base, e->d_view_bits, e->d_segff, e->max_segs,
-                                                                                                    e->d_header, (int)e->header.size(), offsets, out, e->d_overflow);
-    g_launches.fetch_add(9);
+    jpeg_pack_kernel<<<dim3((unsigned)e->max_segs, (unsigned)n), 256, 0, st>>>(e->d_stream, e->d_word_base, e->d_view_bits, e->d_segff, e->max_segs,
+                                                                             e->d_header, (int)e->header.size(), offsets, out, e->d_overflow);
+    g_launches.fetch_add(10);
     CU(cudaGetLastError());
     return X360_OK;
 }
@@ -1674,7 +1674,7 @@ int x360_jpeg_create(int32_t device, int32_t h, int32_t w, int32_t max_images, i
     // 5-15 % of that and of uniform noise 40 %; a batch that needs more is refused (X360_E_NOMEM), not truncated.
     const size_t raw = (size_t)h * w * 3;
     e->max_segs = (int)((raw + raw / 2 + 4096 + kJpegSeg - 1) / kJpegSeg);          // per view: 1.5 x its raw size
-    e->cap_words = ((unsigned long long)raw * (unsigned long long)max_images) / 4ull + 2ull * (unsigned long long)max_images + 1024ull;
+    e->cap_words = (((unsigned long long)raw * (unsigned long long)max_images) / 4ull + 8ull * (unsigned long long)max_images + 1024ull + 3ull) & ~3ull;
     JpegHuff hf;
     jpeg_make_huff(&hf);
     cudaError_t c = cudaMemcpyToSymbol(c_jpeg_huff, &hf, sizeof hf);
@@ -1774,7 +1774,7 @@ int x360_jpeg_coefficients_host(x360_jpeg *e, const uint8_t *images, int32_t n_i
     if (!e->d_images) CU(cudaMalloc(&e->d_images, img * e->max_images));
     CU(cudaMemcpy(e->d_images, images, img * n_images, cudaMemcpyHostToDevice));
     const JpegGeom &g = e->g;
-    jpeg_blocks_kernel<<<dim3((unsigned)((g.n_blocks + 127) / 128), (unsigned)n_images), 128>>>(e->d_images, g, e->tab, e->d_coef);
+    jpeg_blocks_kernel<<<dim3((unsigned)((g.mw + kJbMcus - 1) / kJbMcus), (unsigned)g.mh, (unsigned)n_images), kJbThreads>>>(e->d_images, g, e->tab, e->d_coef);
     jpeg_dummy_dc_kernel<<<dim3((unsigned)((g.n_mcu + 127) / 128), (unsigned)n_images), 128>>>(g, e->d_coef);
     g_launches.fetch_add(2);
     CU(cudaGetLastError());
