@@ -1367,9 +1367,17 @@ int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, ui
     if (n_frames == 0) return X360_OK;
     CU(cudaSetDevice(pl->p.device));
     if (int rc = pipe_setup(pl)) return rc;
+    // Chunks of pl->chunk frames, with a half chunk first and last where the batch is long enough: the pipeline's fill (the
+    // first upload, nothing to overlap it with) and drain (the last download) are then half as long.
     int rc = X360_OK, c = 0;
-    for (int f0 = 0; f0 < n_frames && rc == X360_OK; f0 += pl->chunk, ++c)
-        rc = pipe_chunk(pl, c, frames, f0, (n_frames - f0 < pl->chunk) ? n_frames - f0 : pl->chunk, out_views, sum_lap, sum_lap2);
+    const int half = pl->chunk / 2 > 0 ? pl->chunk / 2 : 1;
+    const bool ramp = pl->chunk >= 2 && n_frames >= 2 * pl->chunk;
+    for (int f0 = 0; f0 < n_frames && rc == X360_OK; ++c) {
+        int n = n_frames - f0 < pl->chunk ? n_frames - f0 : pl->chunk;
+        if (ramp && (f0 == 0 || n_frames - f0 <= pl->chunk) && n > half) n = half;
+        rc = pipe_chunk(pl, c, frames, f0, n, out_views, sum_lap, sum_lap2);
+        f0 += n;
+    }
     // Drain all three streams on EVERY exit: copies still in flight target the caller's buffers, which it may free as
     // soon as this function has returned (with an error as much as with success).
     const std::string first_error = rc != X360_OK ? g_err : std::string();
