@@ -2,6 +2,11 @@
 regular TMA box, a wide box, a seam box, or the direct gathers — from the exact Q5 maps of the oracle's cv2 path.
 
     python scripts/footprint_survey.py cfg1 [cfg4 ...]      (CPU only; workloads of bench.py)
+
+A model of the mid-round-2 kernel: one capacity for all views (that of the group serving view 0), 64-byte raw classes and
+upright 32 x th tiles everywhere.  The shipped kernel has since gained per-group capacities, the skewed class widths of the
+general group (48 / 112 / 176 / 240) and transposed tiles; its own counts are `Extractor.tile_modes()` /
+`Extractor.transposed_blocks()` after a launch (bench.py: `roofline.tile_modes`).
 """
 import importlib
 import json
