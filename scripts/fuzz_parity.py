@@ -43,6 +43,8 @@ def run(n_cases=200, seed=2024, verbose=True):
             W = 2 * H
             d = int(rng.integers(64, 200))
             F = min(F, 3)
+        if rng.random() < 0.3:                             # whole 32 x 32 blocks: general views may take transposed tiles
+            d = max(32, (d + 31) // 32 * 32)
         frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
         views = x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout)
         names, R = x360.rotation_stack(views)
@@ -59,6 +61,7 @@ def run(n_cases=200, seed=2024, verbose=True):
                     got, _ = ex.extract(frames, want_scores=False)
                     ok = np.array_equal(got, want)
                 modes = ex.tile_modes()
+                modes["transposed_blocks"] = ex.transposed_blocks()
         except Exception as e:                            # noqa: BLE001 - the report carries the message
             ok, modes = False, {"error": str(e)}
         report["cases"] += 1
