@@ -1048,15 +1048,17 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
                 // survey finds enough of them to fill that launch's grid several times over: measured neutral on cfg4 (~5000
                 // pairs, direct share 12 % -> 2 %), 10 % slower on cfg1 (~1100 pairs: two half-empty waves), so small jobs keep
                 // the direct gathers for those tiles.
-                const int rows2 = lab_int("X360_T2_ROWS", 64), bw2 = lab_int("X360_T2_BW", raw ? tiled_box_bw(true, G.col_u0, 3) : 240);
-                if (!lz && !(raw && G.col_u0) && !pl->opts.no_wide && rows2 * bw2 > rows * bw && !lab_int("X360_ONE_LAUNCH", 0)) {
+                // Lanczos4 (single-frame jobs, 8 x 8 taps: a direct tile costs 64 global loads per pixel): 80-row buffers, used from
+                // one wave of such pairs on — cfg3 21.5 -> 23.0 Gpix/s, direct share 11.5 % -> 3 %.
+                const int rows2 = lab_int("X360_T2_ROWS", lz ? 80 : 64), bw2 = lab_int("X360_T2_BW", raw ? tiled_box_bw(true, G.col_u0, 3) : 240);
+                if (!(raw && G.col_u0) && !pl->opts.no_wide && rows2 * bw2 > rows * bw && !lab_int("X360_ONE_LAUNCH", 0)) {
                     G.t2_rows[sc] = rows2;
                     G.t2_bw[sc] = bw2;
                     wide_class_rows(rows2, bw2, G.wide_rows2[sc]);
                     G.t2_smem[sc] = tiled_smem_bytes(rows2, bw2, sc != 0, lz, th, G.col_u0, raw);
                     if (G.t2_smem[sc] <= (size_t)kTiledSmemCap) {
                         G.grid_cap2[sc] = pl->sm_count * tiled_occupancy(pl, G, sc, G.t2_smem[sc]);
-                        G.two_launch[sc] = unfit >= (long long)lab_int("X360_DEFER_MIN_WAVES", 4) * G.grid_cap2[sc];
+                        G.two_launch[sc] = unfit >= (long long)lab_int("X360_DEFER_MIN_WAVES", lz ? 1 : 4) * G.grid_cap2[sc];
                     }
                 }
             }

@@ -498,6 +498,28 @@ def test_transposed_tiles_against_oracle(x360, oracle, cfg):
         assert_same(ex.extract(frames, want_scores=False)[0], want, f"{cfg} 32-row tiles")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(1024, 2048, 512, 90, "cube", 6, 0, 1), (960, 1920, 448, 100, "fibonacci", 9, -20, 2)])
+def test_lanczos_second_launch_against_oracle(x360, oracle, cfg):
+    """Lanczos4 plans defer the (tile, view) pairs that fit no staging box to a second launch with larger buffers (from one wave
+    of them on): same bytes as the oracle and as the plan without it (FLAG_NO_WIDE), fewer pairs on the direct gathers."""
+    H, W, d, fov, layout, n, pitch, F = cfg
+    frames = np.stack([noise_frame(1500 + i, H, W) for i in range(F)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(n, pitch_offset=pitch, layout_mode=layout))
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, 1, want_scores=True)
+    modes = {}
+    for name, flags in (("auto", 0), ("no_wide", x360.FLAG_NO_WIDE)):
+        with x360.Extractor(H, W, d, fov, R, "lanczos", max_batch=F, flags=flags) as ex:
+            got, _ = ex.extract(frames, want_scores=False)
+            modes[name] = ex.tile_modes()
+            assert_same(got, want, f"{cfg} {name}", LANCZOS_TOL_LSB)
+            got, s, s2 = ex.extract_sums(frames)
+            assert_same(got, want, f"{cfg} {name} with scores", LANCZOS_TOL_LSB)
+            assert np.array_equal(s, ws) and np.array_equal(s2, ws2), f"{cfg} {name}: integer Laplacian sums"
+    direct = lambda m: m["direct_aligned"] + m["direct_bytewise"]
+    assert direct(modes["auto"]) < direct(modes["no_wide"]), modes
+
+
 def test_two_live_plans_do_not_break_each_other(x360, oracle):
     """The dynamic shared-memory limit belongs to the kernel function: a second, smaller plan must not lower it under a live
     larger one (BlurAnalyzer / create_rectilinear_map build temporary plans while a session is alive)."""
