@@ -434,10 +434,12 @@ __device__ __forceinline__ void transform_group(const uint8_t *src, uint8_t *dst
 // transposition through 18 KB of shared memory, 8 LDS.128 per pixel: 64 of the kernel's 204 shared-memory wavefronts per 32
 // pixels, with the LSU pipe 90 % busy and the issue slots 26 %).  Round 2 COMPUTES the 64 weights in registers from what the
 // table is made of (x360_tables.hpp): it[r][c] = sat_s16(rint(f32(k[fy][r] * k[fx][c]) * 2^15)), plus the residue the table's
-// sum-to-2^15 fix-up puts on one of the taps (4..5, 4..5).  FMUL.RN gives the float32 product; FFMA(p, 2^15, 1.5 * 2^23)
-// rounds p * 2^15 (exact) to the nearest even integer in the low mantissa bits — the low 16 bits ARE the int16 weight, and a
-// PRMT packs two of them.  The only product that saturates is 1.0 * 1.0 (fy = fx = 0, tap (3, 3)): clamped explicitly.
-__device__ __forceinline__ uint32_t lz_weight_bits(float cy, float cx) { return __float_as_uint(fmaf(__fmul_rn(cy, cx), 32768.0f, 12582912.0f)); }
+// sum-to-2^15 fix-up puts on one of the taps (4..5, 4..5).  FFMA(k[fy][r], k[fx][c] * 2^15, 1.5 * 2^23) rounds the exact
+// product to the nearest even integer in the low mantissa bits — the low 16 bits ARE the int16 weight, and a PRMT packs two of
+// them.  (OpenCV rounds twice — the product to float32, then to the integer; for all 65 536 entries of this table the single
+// rounding gives the same integer: tests/test_host_api.py checks it exhaustively, so one FFMA replaces FMUL + FFMA.)  The only
+// product that saturates is 1.0 * 1.0 (fy = fx = 0, tap (3, 3)): clamped explicitly.
+__device__ __forceinline__ uint32_t lz_weight_bits(float cy, float cx_q15) { return __float_as_uint(fmaf(cy, cx_q15, 12582912.0f)); }
 
 __device__ __forceinline__ uint32_t lanczos_pairs(const uint8_t *dsm, uint32_t a0, uint32_t ppitch, const float *__restrict__ k1,
                                                   const uint32_t *__restrict__ fix, uint32_t idx)
@@ -445,7 +447,8 @@ __device__ __forceinline__ uint32_t lanczos_pairs(const uint8_t *dsm, uint32_t a
     const uint32_t fx = idx & 31u, fy = idx >> 5;
     const float4 xa = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fx)), xb = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fx) + 1);
     const float4 ya = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fy)), yb = __ldg(reinterpret_cast<const float4 *>(k1 + 8 * fy) + 1);
-    const float cx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float cx[8] = {xa.x * 32768.0f, xa.y * 32768.0f, xa.z * 32768.0f, xa.w * 32768.0f,       // (exact: a power of two)
+                         xb.x * 32768.0f, xb.y * 32768.0f, xb.z * 32768.0f, xb.w * 32768.0f};
     const float cy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
     const uint32_t fw = __ldg(fix + idx);
     const uint32_t fpos = fw & 3u, fdelta = (uint32_t)((int)fw >> 16);                 // residue as a two's-complement word

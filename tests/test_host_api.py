@@ -376,6 +376,10 @@ def test_lanczos4_factors_rebuild_the_table(x360):
     assert np.array_equal(tab.reshape(1024, 8, 8), c_oracle.lanczos4_table().reshape(1024, 8, 8))
     assert (v.reshape(1024, 64).sum(axis=1) == 32768).all()                          # what the fix-up is for
     assert np.count_nonzero(delta) == 856                                            # 856 of 1024 entries are fixed up
+    # the kernel fuses the product and the rounding into ONE FFMA(k[fy][r], k[fx][c] * 2^15, 1.5 * 2^23): a single rounding of
+    # the exact product instead of OpenCV's two (to float32, then to the integer) — the same integer for every entry of the table
+    exact = k[:, None, :, None].astype(np.float64) * k[None, :, None, :].astype(np.float64) * 32768.0     # exact in fp64 (24 + 24 bits)
+    assert np.array_equal(np.rint(exact), np.rint(p.astype(np.float64) * 32768.0))
 
 
 def test_c_blur_machine_equals_the_python_replay(x360):
