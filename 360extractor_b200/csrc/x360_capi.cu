@@ -625,6 +625,8 @@ struct x360_plan {
     uint8_t *d_jpeg[2] = {};
     long long *d_joff[2] = {}, *h_joff[2] = {};
     long long *h_sums[2] = {};           // filtered host path: the chunk's sum pairs, pinned
+    long long *h_sum_stage = nullptr;    // x360_extract_host: the call's sum pairs, pinned (a copy into the caller's pageable arrays
+    size_t h_sum_stage_cap = 0;          // would block the host until the chunk's download ends, and the next upload behind it)
     long long jpeg_cap = 0;
     cudaStream_t s_off = nullptr;
     cudaEvent_t ev_off[2] = {};
@@ -1194,6 +1196,7 @@ int x360_plan_destroy(x360_plan *pl)
         cudaFree(pl->d_joff[i]);
         if (pl->h_joff[i]) cudaFreeHost(pl->h_joff[i]);
         if (pl->h_sums[i]) cudaFreeHost(pl->h_sums[i]);
+        if (i == 0 && pl->h_sum_stage) cudaFreeHost(pl->h_sum_stage);
         if (pl->ev_off[i]) cudaEventDestroy(pl->ev_off[i]);
     }
     if (pl->s_off) cudaStreamDestroy(pl->s_off);
@@ -1369,6 +1372,19 @@ int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, ui
     if (n_frames == 0) return X360_OK;
     CU(cudaSetDevice(pl->p.device));
     if (int rc = pipe_setup(pl)) return rc;
+    // the sums travel through pinned memory and reach the caller's arrays after the drain
+    const size_t n_sums = (size_t)n_frames * pl->p.n_views;
+    int64_t *st_lap = nullptr, *st_lap2 = nullptr;
+    if (sum_lap) {
+        if (pl->h_sum_stage_cap < 2 * n_sums) {
+            if (pl->h_sum_stage) cudaFreeHost(pl->h_sum_stage);
+            pl->h_sum_stage = nullptr; pl->h_sum_stage_cap = 0;
+            CU(cudaHostAlloc(&pl->h_sum_stage, sizeof(long long) * 2 * n_sums, cudaHostAllocDefault));
+            pl->h_sum_stage_cap = 2 * n_sums;
+        }
+        st_lap = (int64_t *)pl->h_sum_stage;
+        st_lap2 = st_lap + n_sums;
+    }
     // Chunks of pl->chunk frames, with a half chunk first and last where the batch is long enough: the pipeline's fill (the
     // first upload, nothing to overlap it with) and drain (the last download) are then half as long.
     int rc = X360_OK, c = 0;
@@ -1377,7 +1393,7 @@ int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, ui
     for (int f0 = 0; f0 < n_frames && rc == X360_OK; ++c) {
         int n = n_frames - f0 < pl->chunk ? n_frames - f0 : pl->chunk;
         if (ramp && (f0 == 0 || n_frames - f0 <= pl->chunk) && n > half) n = half;
-        rc = pipe_chunk(pl, c, frames, f0, n, out_views, sum_lap, sum_lap2);
+        rc = pipe_chunk(pl, c, frames, f0, n, out_views, st_lap, st_lap2);
         f0 += n;
     }
     // Drain all three streams on EVERY exit: copies still in flight target the caller's buffers, which it may free as
@@ -1387,6 +1403,10 @@ int x360_extract_host(x360_plan *pl, const uint8_t *frames, int32_t n_frames, ui
     if (rc != X360_OK) { g_err = first_error; return rc; }
     for (cudaError_t e : {e_out, e_k, e_in})
         if (e != cudaSuccess) return fail(X360_E_CUDA, "pipelined extraction failed: %s", cudaGetErrorString(e));
+    if (sum_lap) {
+        memcpy(sum_lap, st_lap, sizeof(int64_t) * n_sums);
+        memcpy(sum_lap2, st_lap2, sizeof(int64_t) * n_sums);
+    }
     return X360_OK;
 }
 
@@ -1825,6 +1845,18 @@ int x360_extract_host_jpeg(x360_plan *pl, const uint8_t *frames, int32_t n_frame
     }
     const size_t fb = (size_t)pl->g.H * pl->g.W * 3;
     const bool scores = sum_lap != nullptr;
+    const size_t n_sums = (size_t)n_frames * V;
+    int64_t *st_lap = nullptr, *st_lap2 = nullptr;
+    if (scores) {
+        if (pl->h_sum_stage_cap < 2 * n_sums) {
+            if (pl->h_sum_stage) cudaFreeHost(pl->h_sum_stage);
+            pl->h_sum_stage = nullptr; pl->h_sum_stage_cap = 0;
+            CU(cudaHostAlloc(&pl->h_sum_stage, sizeof(long long) * 2 * n_sums, cudaHostAllocDefault));
+            pl->h_sum_stage_cap = 2 * n_sums;
+        }
+        st_lap = (int64_t *)pl->h_sum_stage;
+        st_lap2 = st_lap + n_sums;
+    }
     long long base = 0;
     int rc = X360_OK;
     // finish chunk c: its offsets are on the host -> the size of its files is known -> download exactly those bytes
@@ -1863,9 +1895,9 @@ int x360_extract_host_jpeg(x360_plan *pl, const uint8_t *frames, int32_t n_frame
             CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
             CU(cudaStreamWaitEvent(pl->s_off, pl->ev_k[b], 0));
             CU(cudaMemcpyAsync(pl->h_joff[b], pl->d_joff[b], sizeof(long long) * ((size_t)m + 2), cudaMemcpyDeviceToHost, pl->s_off));
-            if (scores) {
-                CU(cudaMemcpyAsync(sum_lap + (size_t)f0 * V, ds, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
-                CU(cudaMemcpyAsync(sum_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
+            if (scores) {                                                       // (pinned staging: see x360_extract_host)
+                CU(cudaMemcpyAsync(st_lap + (size_t)f0 * V, ds, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
+                CU(cudaMemcpyAsync(st_lap2 + (size_t)f0 * V, ds2, sizeof(long long) * m, cudaMemcpyDeviceToHost, pl->s_off));
             }
             CU(cudaEventRecord(pl->ev_off[b], pl->s_off));
             return X360_OK;
@@ -1880,6 +1912,10 @@ int x360_extract_host_jpeg(x360_plan *pl, const uint8_t *frames, int32_t n_frame
     if (rc != X360_OK) { g_err = first_error; return rc; }
     for (cudaError_t e : {e_out, e_off, e_k, e_in})
         if (e != cudaSuccess) return fail(X360_E_CUDA, "pipelined extraction failed: %s", cudaGetErrorString(e));
+    if (scores) {
+        memcpy(sum_lap, st_lap, sizeof(int64_t) * n_sums);
+        memcpy(sum_lap2, st_lap2, sizeof(int64_t) * n_sums);
+    }
     return X360_OK;
 }
 

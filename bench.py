@@ -408,6 +408,25 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
                       "h2d_bytes_per_step": F * H * W * 3, "d2h_bytes_per_step": F * V * d * d * 3 + (16 * F * V if wl["scores"] else 0),
                       "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                       "api": "Extractor.extract(pinned numpy) -> x360_extract_host (chunked H2D / kernel / D2H on side streams)"}
+        if wl["scores"]:
+            # the blur filter on (src/core/processor.py:341-376, plain threshold at the batch's median score): only the views the
+            # machine keeps cross PCIe on the way back — sums first, the host replays the machine one chunk behind the GPU
+            cap = pkg._capi
+            _, _, s_all = ex.extract_filtered(pin_in.array, _blur_state(cap, False, 0.0), out=pin_out.array.reshape(F * V, d, d, 3))
+            thr = float(np.median(s_all))
+            kept = 0
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                kv, keep, _ = ex.extract_filtered(pin_in.array, _blur_state(cap, False, thr), out=pin_out.array.reshape(F * V, d, d, 3))
+                kept = int(keep.sum())
+            torch.cuda.synchronize()
+            f_s = time.perf_counter() - t0
+            res["e2e_filtered"] = {"value": out_pix_per_step * e2e_steps / f_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * 3,
+                                   "d2h_bytes_per_step": kept * d * d * 3 + 16 * F * V, "views_kept": kept, "views_total": F * V,
+                                   "blur_filter": {"smart": False, "threshold": thr, "note": "median score of the batch: about half the views are kept"},
+                                   "steps": e2e_steps, "ms_per_step": 1e3 * f_s / e2e_steps,
+                                   "api": "Extractor.extract_filtered(pinned numpy, blur state) -> x360_extract_host_filtered (value counts every extracted view, kept or not, as the reference's loop does)"}
         pin_out.free()
         if with_jpeg:
             # the same call with the reference's save step on the device: frames in, the .jpg files (quality 95, byte-identical
@@ -440,6 +459,12 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
     del d_frames, d_out
     torch.cuda.empty_cache()
     return res
+
+
+def _blur_state(cap, smart, threshold):
+    st = cap.BlurState()
+    cap.lib().x360_blur_state_init(st, 1, int(smart), float(threshold))
+    return st
 
 
 def bench_sharded_cfg4(pkg, torch, dist, args, dev, local_rank, rank, world):
@@ -601,6 +626,8 @@ def main():
         }
         if "roofline_int" in main_res:
             line["roofline_int"] = main_res["roofline_int"]
+        if "e2e_filtered" in main_res:
+            line["e2e_filtered"] = main_res["e2e_filtered"]
         if world == 1 and extra:
             line["configs"] = extra
         else:
