@@ -8,7 +8,7 @@ Laplacian-variance blur score.  All pixel work runs in hand-written CUDA behind 
 The directory name starts with a digit, so import it with
 ``importlib.import_module("360extractor_b200")`` or through the ``x360`` alias at the repo root.
 """
-from ._capi import (FLAG_FUSED_SCORE, FLAG_NO_WIDE, FLAG_PLANES, FLAG_SPLIT_SCORE, FLAG_TILE_H16, FLAG_TILE_H32, INTERP_LANCZOS4,
+from ._capi import (FLAG_FULL_UPLOAD, FLAG_FUSED_SCORE, FLAG_NO_WIDE, FLAG_PLANES, FLAG_SPLIT_SCORE, FLAG_TILE_H16, FLAG_TILE_H32, INTERP_LANCZOS4,
                     INTERP_LINEAR, X360Error, launch_count, version)
 from .analyzer import BlurAnalyzer
 from .blur_filter import BlurFilter
@@ -30,5 +30,5 @@ __all__ = [
     "gather_sums", "gather_sums_by_view", "shard_axis", "shard_bounds", "shard_sizes",
     "normalize_mask_faces", "eligible_indices", "masker_slots", "masker_input", "scatter_results",
     "INTERP_LINEAR", "INTERP_LANCZOS4", "X360Error", "launch_count", "version",
-    "FLAG_PLANES", "FLAG_FUSED_SCORE", "FLAG_SPLIT_SCORE", "FLAG_TILE_H16", "FLAG_TILE_H32", "FLAG_NO_WIDE",
+    "FLAG_PLANES", "FLAG_FUSED_SCORE", "FLAG_SPLIT_SCORE", "FLAG_TILE_H16", "FLAG_TILE_H32", "FLAG_NO_WIDE", "FLAG_FULL_UPLOAD",
 ]

@@ -12,7 +12,7 @@ X360_OK = 0
 INTERP_LINEAR = 0
 INTERP_LANCZOS4 = 1
 PATH_AUTO, PATH_DIRECT, PATH_STAGED, PATH_TILED = 0, 1, 2, 3
-FLAG_PLANES, FLAG_FUSED_SCORE, FLAG_SPLIT_SCORE, FLAG_TILE_H16, FLAG_TILE_H32, FLAG_NO_WIDE = 1, 2, 4, 8, 16, 32
+FLAG_PLANES, FLAG_FUSED_SCORE, FLAG_SPLIT_SCORE, FLAG_TILE_H16, FLAG_TILE_H32, FLAG_NO_WIDE, FLAG_FULL_UPLOAD = 1, 2, 4, 8, 16, 32, 64
 
 
 class X360Error(RuntimeError):
@@ -92,6 +92,7 @@ SYMBOLS = {
     "x360_plan_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(_i32)] * 4),
     "x360_plan_tile_modes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint32)]),
     "x360_plan_transposed_blocks": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64)]),
+    "x360_plan_upload_rows": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
 }
 
 _lib = None

@@ -201,6 +201,7 @@ struct PlanOpts {
     int score_mode = 0;         // 0 = the plan's default, 1 = fused into the extraction kernel, 2 = split pass over the views
     int force_th = 0;           // 16 / 32: output tile height
     bool no_wide = false;       // no wide / seam boxes
+    bool full_upload = false;   // host entries upload whole frames
 };
 PlanOpts plan_opts(int flags)
 {
@@ -211,6 +212,7 @@ PlanOpts plan_opts(int flags)
     if (lab_int("X360_RAW_SCORES", 0)) o.score_mode = 1;
     o.force_th = (flags & X360_FLAG_TILE_H16) ? 16 : ((flags & X360_FLAG_TILE_H32) ? 32 : lab_int("X360_TILED_TH", 0));
     o.no_wide = (flags & X360_FLAG_NO_WIDE) != 0 || lab_int("X360_NO_WIDE", 0) != 0;
+    o.full_upload = (flags & X360_FLAG_FULL_UPLOAD) != 0;
     return o;
 }
 // Score policy.  By default the blur score is a second, streaming pass over the finished views (blur_sums_march_kernel: warp
@@ -625,6 +627,7 @@ struct x360_plan {
     uint8_t *d_jpeg[2] = {};
     long long *d_joff[2] = {}, *h_joff[2] = {};
     long long *h_sums[2] = {};           // filtered host path: the chunk's sum pairs, pinned
+    int up_row0 = 0, up_rows = 0;         // the band of source rows the host entries upload (x360_plan_upload_rows)
     long long *h_sum_stage = nullptr;    // x360_extract_host: the call's sum pairs, pinned (a copy into the caller's pageable arrays
     size_t h_sum_stage_cap = 0;          // would block the host until the chunk's download ends, and the next upload behind it)
     long long jpeg_cap = 0;
@@ -1141,6 +1144,30 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         }
     }
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_R, params->R, sizeof(double) * 9 * params->n_views, cudaMemcpyHostToDevice);
+    // the band of source rows the views can read: min / max of floor(map_y) over every output pixel (the kernel's own map),
+    // widened by the taps and two rows of margin; a band that wraps (a view sees a pole) or covers most of the frame: all rows
+    pl->up_row0 = 0;
+    pl->up_rows = params->src_h;
+    if (e == cudaSuccess && !pl->opts.full_upload) {
+        const int init[2] = {INT_MAX, INT_MIN};
+        int lohi[2] = {0, 0};
+        int *d_lohi = reinterpret_cast<int *>(pl->d_modes);                 // (scratch, zeroed again below)
+        e = cudaMemcpy(d_lohi, init, sizeof init, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            source_row_range_kernel<<<dim3((unsigned)((pl->g.ow + 31) / 32), (unsigned)((pl->g.oh + 7) / 8), (unsigned)params->n_views), 256>>>(pl->g, pl->d_R, d_lohi);
+            g_launches.fetch_add(1);
+            e = cudaMemcpy(lohi, d_lohi, sizeof lohi, cudaMemcpyDeviceToHost);
+        }
+        if (e == cudaSuccess) e = cudaMemset(pl->d_modes, 0, sizeof(unsigned) * kRingSlots * kRingWords);
+        if (e == cudaSuccess) {
+            const bool lz = params->interp == X360_INTERP_LANCZOS4;
+            const int t_lo = lz ? 3 : 0, t_hi = lz ? 4 : 1, margin = 2;
+            if (lohi[0] - t_lo >= 0 && lohi[1] + t_hi <= params->src_h - 1) {
+                const int r0 = std::max(0, lohi[0] - t_lo - margin), r1 = std::min(params->src_h - 1, lohi[1] + t_hi + margin);
+                if ((long long)(r1 - r0 + 1) * 10 < (long long)params->src_h * 9) { pl->up_row0 = r0; pl->up_rows = r1 - r0 + 1; }
+            }
+        }
+    }
     if (e == cudaSuccess && params->interp == X360_INTERP_LANCZOS4) {
         const std::vector<int16_t> t = lanczos4_q15_table();
         e = cudaMalloc(&pl->d_lz, t.size() * sizeof(int16_t));
@@ -1233,6 +1260,14 @@ int x360_plan_info(const x360_plan *pl, int32_t *path, int32_t *grid, int32_t *b
     if (block) *block = pl->path == X360_PATH_TILED ? 32 * tiled_warps(false, pl->grp[0].t_th[0]) : kThreads;
     if (smem_bytes) *smem_bytes = pl->path == X360_PATH_TILED ? (int32_t)pl->grp[0].t_smem[0]
                                   : (pl->path == X360_PATH_STAGED ? (int32_t)pl->smem : (int32_t)sizeof(TileSmem));
+    return X360_OK;
+}
+
+int x360_plan_upload_rows(const x360_plan *pl, int32_t *first_row, int32_t *n_rows)
+{
+    if (!pl) return fail(X360_E_INVALID, "null argument");
+    if (first_row) *first_row = pl->up_row0;
+    if (n_rows) *n_rows = pl->up_rows;
     return X360_OK;
 }
 
@@ -1330,6 +1365,19 @@ static int pipe_setup(x360_plan *pl)
     return X360_OK;
 }
 
+// n frames from the caller's host memory into a chunk buffer: whole frames, or only the rows the views can read
+static cudaError_t upload_frames(const x360_plan *pl, uint8_t *dst, const uint8_t *src, int n, cudaStream_t st)
+{
+    const size_t pitch = (size_t)pl->g.W * 3, fb = pitch * pl->g.H;
+    if (pl->up_rows >= pl->g.H) return cudaMemcpyAsync(dst, src, fb * n, cudaMemcpyHostToDevice, st);
+    const size_t off = (size_t)pl->up_row0 * pitch, bytes = (size_t)pl->up_rows * pitch;
+    for (int i = 0; i < n; ++i) {
+        const cudaError_t e = cudaMemcpyAsync(dst + (size_t)i * fb + off, src + (size_t)i * fb + off, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // one chunk of the pipeline (see x360_extract_host); any failure is reported to the caller, which drains the streams
 static int pipe_chunk(x360_plan *pl, int c, const uint8_t *frames, int f0, int n, uint8_t *out_views, int64_t *sum_lap, int64_t *sum_lap2)
 {
@@ -1338,7 +1386,7 @@ static int pipe_chunk(x360_plan *pl, int c, const uint8_t *frames, int f0, int n
     const bool scores = sum_lap != nullptr;
     // upload: the input buffer is free once the kernel of chunk c-2 has run
     if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
-    CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+    CU(upload_frames(pl, pl->d_frames[b], frames + (size_t)f0 * fb, n, pl->s_in));
     CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
     // compute: needs the upload, and the download of chunk c-2 out of this output buffer
     CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
@@ -1877,7 +1925,7 @@ int x360_extract_host_jpeg(x360_plan *pl, const uint8_t *frames, int32_t n_frame
         const int b = c & 1, f0 = c * pl->chunk, n = std::min(pl->chunk, n_frames - f0), m = n * V;
         auto enqueue = [&]() -> int {
             if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
-            CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+            CU(upload_frames(pl, pl->d_frames[b], frames + (size_t)f0 * fb, n, pl->s_in));
             CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
             CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
             if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));       // the files of chunk c-2 have left d_jpeg[b]
@@ -2008,7 +2056,7 @@ int x360_extract_host_filtered(x360_plan *pl, const uint8_t *frames, int32_t n_f
         const int b = c & 1, f0 = c * pl->chunk, n = std::min(pl->chunk, n_frames - f0), m = n * V;
         auto enqueue = [&]() -> int {
             if (c >= 2) CU(cudaStreamWaitEvent(pl->s_in, pl->ev_k[b], 0));
-            CU(cudaMemcpyAsync(pl->d_frames[b], frames + (size_t)f0 * fb, fb * n, cudaMemcpyHostToDevice, pl->s_in));
+            CU(upload_frames(pl, pl->d_frames[b], frames + (size_t)f0 * fb, n, pl->s_in));
             CU(cudaEventRecord(pl->ev_in[b], pl->s_in));
             CU(cudaStreamWaitEvent(pl->s_k, pl->ev_in[b], 0));
             if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));       // the kept views of chunk c-2 have left this buffer

@@ -21,6 +21,25 @@ make_maps_kernel(const Geom g, const double *__restrict__ R, float *__restrict__
     map_y[(size_t)y * g.ow + x] = my;
 }
 
+// min / max of floor(map_y) over every output pixel of every view (plan creation: the host entries upload only the source rows
+// the views can read, x360_plan_upload_rows).  lohi[0] starts at INT_MAX, lohi[1] at INT_MIN.
+__global__ void __launch_bounds__(256)
+source_row_range_kernel(const Geom g, const double *__restrict__ R, int *__restrict__ lohi)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    int lo = INT_MAX, hi = INT_MIN;
+    if (x < g.ow && y < g.oh) {
+        double uf;
+        float my;
+        map_f64(R + 9 * blockIdx.z, g, x, y, uf, my);
+        lo = hi = q5_of(my) >> 5;
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&lohi[0], lo); atomicMax(&lohi[1], hi); }
+}
+
 // cv2.remap(frame, map_x, map_y, interp, borderMode=BORDER_WRAP) with caller-held maps
 // (src/core/processor.py:334, src/core/analyzer.py:63).
 template <class S>

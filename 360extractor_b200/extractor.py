@@ -149,6 +149,13 @@ class Extractor:
         return {"staged": int(out[0]), "direct_aligned": int(out[1]), "direct_bytewise": int(out[2]),
                 "staged_wide": int(out[3]), "staged_seam": int(out[4])}
 
+    def upload_rows(self):
+        """``(first_row, n_rows)``: the band of source rows the host entries upload per frame (the rows the views can read;
+        the whole frame for plans that see a pole, and with ``FLAG_FULL_UPLOAD``)."""
+        r0, n = ctypes.c_int32(), ctypes.c_int32()
+        check(lib().x360_plan_upload_rows(self._plan, ctypes.byref(r0), ctypes.byref(n)))
+        return int(r0.value), int(n.value)
+
     def transposed_blocks(self):
         """32 x 32 output blocks (over all views) the plan gathers with the lanes running down the rows (pole-face quadrants
         where the source row changes faster along x than along y); a layout choice, the pixels are the same."""

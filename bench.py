@@ -405,9 +405,10 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         res["e2e"] = {"value": out_pix_per_step * e2e_steps / e2e_s / 1e6, "unit": "Mpix/s",
-                      "h2d_bytes_per_step": F * H * W * 3, "d2h_bytes_per_step": F * V * d * d * 3 + (16 * F * V if wl["scores"] else 0),
+                      "h2d_bytes_per_step": F * ex.upload_rows()[1] * W * 3, "d2h_bytes_per_step": F * V * d * d * 3 + (16 * F * V if wl["scores"] else 0),
                       "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                      "api": "Extractor.extract(pinned numpy) -> x360_extract_host (chunked H2D / kernel / D2H on side streams)"}
+                      "uploaded_rows": list(ex.upload_rows()), "src_rows": H,
+                      "api": "Extractor.extract(pinned numpy) -> x360_extract_host (chunked H2D of the source rows the views read / kernel / D2H on side streams)"}
         if wl["scores"]:
             # the blur filter on (src/core/processor.py:341-376, plain threshold at the batch's median score): only the views the
             # machine keeps cross PCIe on the way back — sums first, the host replays the machine one chunk behind the GPU
@@ -422,7 +423,7 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
                 kept = int(keep.sum())
             torch.cuda.synchronize()
             f_s = time.perf_counter() - t0
-            res["e2e_filtered"] = {"value": out_pix_per_step * e2e_steps / f_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * 3,
+            res["e2e_filtered"] = {"value": out_pix_per_step * e2e_steps / f_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": F * ex.upload_rows()[1] * W * 3,
                                    "d2h_bytes_per_step": kept * d * d * 3 + 16 * F * V, "views_kept": kept, "views_total": F * V,
                                    "blur_filter": {"smart": False, "threshold": thr, "note": "median score of the batch: about half the views are kept"},
                                    "steps": e2e_steps, "ms_per_step": 1e3 * f_s / e2e_steps,
@@ -445,7 +446,7 @@ def bench_workload(pkg, torch, dist, args, name, wl, dev, local_rank, rank, worl
                 t = torch.tensor([j_s], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 j_s = float(t.item())
-            res["e2e_encoded"] = {"value": out_pix_per_step * e2e_steps / j_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * 3,
+            res["e2e_encoded"] = {"value": out_pix_per_step * e2e_steps / j_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": F * ex.upload_rows()[1] * W * 3,
                                   "d2h_bytes_per_step": int(total), "jpeg_quality": 95, "bytes_per_output_pixel": total / (F * V * d * d),
                                   "steps": e2e_steps, "ms_per_step": 1e3 * j_s / e2e_steps,
                                   "api": "Extractor.extract_jpeg_into(pinned numpy) -> x360_extract_host_jpeg (H2D / extract / JPEG encode / D2H of the files)",

@@ -79,6 +79,7 @@ typedef struct x360_params {
 #define X360_FLAG_TILE_H16     8   /* 32 x 16 output tiles */
 #define X360_FLAG_TILE_H32    16   /* 32 x 32 output tiles */
 #define X360_FLAG_NO_WIDE     32   /* no wide / seam boxes: tiles beyond the regular staging capacity take the direct gathers */
+#define X360_FLAG_FULL_UPLOAD 64   /* host entries: upload whole frames even where the views read only a band of source rows */
 
 int x360_plan_create(const x360_params *params, x360_plan **out_plan);
 int x360_plan_destroy(x360_plan *plan);
@@ -299,6 +300,11 @@ int x360_plan_tile_modes(x360_plan *plan, uint32_t *out5);
  * rows, because there the source row changes faster along output x than along y (the left / right quadrants of a pole face):
  * a layout choice of the gather, the pixels are the same.  0 for plans without such blocks. */
 int x360_plan_transposed_blocks(const x360_plan *plan, int64_t *n_blocks);
+/* The band of source rows the plan's views can read (every tap of every output pixel, plus a margin): the host entries
+ * (x360_extract_host, _host_jpeg, _host_filtered) upload only these rows of each frame — a ring of 90-degree views at pitch 0
+ * reads half of an equirectangular frame.  [0, src_h) for plans that see a pole or whose band covers most of the frame, and
+ * with X360_FLAG_FULL_UPLOAD.  The device entries read the frames they are given. */
+int x360_plan_upload_rows(const x360_plan *plan, int32_t *first_row, int32_t *n_rows);
 
 #ifdef __cplusplus
 }

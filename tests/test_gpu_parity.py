@@ -520,6 +520,44 @@ def test_lanczos_second_launch_against_oracle(x360, oracle, cfg):
     assert direct(modes["auto"]) < direct(modes["no_wide"]), modes
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["linear", "lanczos"])
+def test_host_path_uploads_only_the_rows_the_views_read(x360, oracle, mode):
+    """A ring at pitch 0 reads a band of source rows: the host entries upload that band only (x360_plan_upload_rows).  The band
+    is sufficient — same views as the oracle — and nothing outside it is read: zeroing the other rows of the frames given to the
+    library changes nothing.  Plans that see a pole, and FLAG_FULL_UPLOAD, take whole frames."""
+    H, W, d, fov, F = 720, 1440, 200, 90, 5
+    frames = np.stack([noise_frame(1700 + i, H, W) for i in range(F)])
+    R = rotations(x360, x360.GeometryProcessor.generate_views(6, 0, "ring"))
+    interp = 1 if mode == "lanczos" else 0
+    want, ws, ws2 = oracle.extract(frames, R, d, fov, interp, want_scores=True)
+    with x360.Extractor(H, W, d, fov, R, mode, max_batch=2) as ex:
+        r0, n = ex.upload_rows()
+        assert 0 < r0 and r0 + n < H and n < 0.75 * H, (r0, n)
+        poisoned = frames.copy()
+        poisoned[:, :r0] = 0
+        poisoned[:, r0 + n:] = 0
+        for src in (frames, poisoned):
+            got, s, s2 = ex.extract_sums(src)
+            assert_same(got, want, f"{mode} band [{r0}, {r0 + n})", LANCZOS_TOL_LSB if interp else 0)
+            assert np.array_equal(s, ws) and np.array_equal(s2, ws2)
+        files, _ = ex.extract_jpeg(poisoned)
+        assert cv2_decode_equal(files[F - 1][len(R) - 1], want[F - 1, len(R) - 1])
+    with x360.Extractor(H, W, d, fov, R, mode, max_batch=2, flags=x360.FLAG_FULL_UPLOAD) as ex:
+        assert ex.upload_rows() == (0, H)
+        assert_same(ex.extract(frames, want_scores=False)[0], want, f"{mode} full upload", LANCZOS_TOL_LSB if interp else 0)
+    Rc = rotations(x360, x360.GeometryProcessor.generate_views(6, 0, "cube"))
+    with x360.Extractor(H, W, d, fov, Rc, mode, max_batch=2) as ex:
+        assert ex.upload_rows() == (0, H)                               # the pole faces read every row
+
+
+def cv2_decode_equal(jpeg_bytes, view):
+    """The file decodes (cv2) to what cv2's own encode of the view decodes to."""
+    import cv2
+    ok, ref = cv2.imencode(".jpg", view, [cv2.IMWRITE_JPEG_QUALITY, 95])
+    return ok and bytes(ref.tobytes()) == bytes(jpeg_bytes)
+
+
 def test_two_live_plans_do_not_break_each_other(x360, oracle):
     """The dynamic shared-memory limit belongs to the kernel function: a second, smaller plan must not lower it under a live
     larger one (BlurAnalyzer / create_rectilinear_map build temporary plans while a session is alive)."""
