@@ -580,6 +580,7 @@ struct TiledGroup {
     TiledUnit *d_units[4] = {};
     int *d_unit_view[4] = {};
     double *d_unit_shift[4] = {};
+    std::vector<int> h_ids;              // the group's plan view indices, ascending (= the order of its one-view units, level 3)
     uint8_t *d_tr_tab = nullptr;         // TiledArgs::tr_tab: [plan views][32 x 32 blocks], or nullptr
     long long n_tr_blocks = 0;
     double rot_inv_pitch[4] = {0, 0, 0, 0};   // TiledArgs::rot_inv_pitch of each level (0: views not evenly spaced, or a general group)
@@ -617,6 +618,11 @@ struct x360_plan {
     int chunk = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
+    // Single-frame chunks of plans whose views share no map (fibonacci, inclined layouts): the views are extracted in view_parts
+    // launches over consecutive view ranges, and each range is downloaded while the next one is computed
+    static constexpr int kViewParts = 4;
+    int view_parts = 1;
+    cudaEvent_t ev_part[2][kViewParts] = {};
     uint8_t *d_frames[2] = {}, *d_views[2] = {}, *d_sharp[2] = {};
     bool sharpen = false;                // x360_extract_host returns unsharp-masked views (scores stay those of the plain views)
     double sharpen_strength = 0.5;
@@ -697,7 +703,7 @@ static int launch_score_pass(x360_plan *pl, const uint8_t *views, int n, int64_t
 // One group's kernel launch(es) of an extract call.  `scratch`: this call's slot of the ring (already zeroed);
 // `gi`: group index (selects the work-item counters inside the slot).
 static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch, const uint8_t *frames, int n_frames, uint8_t *out_views,
-                        int64_t *sum_lap, int64_t *sum_lap2, cudaStream_t st)
+                        int64_t *sum_lap, int64_t *sum_lap2, cudaStream_t st, int v_lo = 0, int v_hi = INT_MAX)
 {
     const bool scores = sum_lap != nullptr;
     const Geom &g = pl->g;
@@ -748,8 +754,16 @@ static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch,
         }
     }
     if (const char *e = lab_env("X360_UNIT_LEVEL")) level = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : level;
-    const int n_units = G.n_units[level];
-    a.units = G.d_units[level];
+    // a view range [v_lo, v_hi) of the plan: the one-view units of this group's views in it (level 3 lists them in view order)
+    int u_begin = 0, n_units = G.n_units[level];
+    if (v_lo > 0 || v_hi < pl->p.n_views) {
+        level = 3;
+        u_begin = (int)(std::lower_bound(G.h_ids.begin(), G.h_ids.end(), v_lo) - G.h_ids.begin());
+        n_units = (int)(std::lower_bound(G.h_ids.begin(), G.h_ids.end(), v_hi) - G.h_ids.begin()) - u_begin;
+        n_chunks = 1;
+        if (n_units <= 0) return X360_OK;
+    }
+    a.units = G.d_units[level] + u_begin;
     a.unit_view = G.d_unit_view[level];
     a.unit_shift = G.d_unit_shift[level];
     a.n_units = n_units;
@@ -813,7 +827,7 @@ static int launch_group(x360_plan *pl, TiledGroup &G, int gi, unsigned *scratch,
 }
 
 static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint8_t *out_views, int64_t *sum_lap,
-                        int64_t *sum_lap2, cudaStream_t st)
+                        int64_t *sum_lap2, cudaStream_t st, int v_lo = 0, int v_hi = INT_MAX)
 {
     if (sum_lap && pl->split_score) {
         // extraction without the fused score, then one streaming pass over the finished views
@@ -832,7 +846,7 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     }
     if (pl->n_groups < 2 || lab_int("X360_SERIAL_GROUPS", 0))  {
         for (int gi = 0; gi < pl->n_groups; ++gi)
-            if (int rc = launch_group(pl, pl->grp[gi], gi, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, st)) return rc;
+            if (int rc = launch_group(pl, pl->grp[gi], gi, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, st, v_lo, v_hi)) return rc;
         return X360_OK;
     }
     // Two groups: the second one (pole faces: the longer items) goes to a side stream forked from the caller's, so that each
@@ -844,8 +858,8 @@ static int launch_tiled(x360_plan *pl, const uint8_t *frames, int n_frames, uint
     }
     CU(cudaEventRecord(pl->ev_fork, st));
     CU(cudaStreamWaitEvent(pl->s_side, pl->ev_fork, 0));
-    int rc = launch_group(pl, pl->grp[1], 1, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, pl->s_side);
-    if (rc == X360_OK) rc = launch_group(pl, pl->grp[0], 0, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, st);
+    int rc = launch_group(pl, pl->grp[1], 1, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, pl->s_side, v_lo, v_hi);
+    if (rc == X360_OK) rc = launch_group(pl, pl->grp[0], 0, scratch, frames, n_frames, out_views, sum_lap, sum_lap2, st, v_lo, v_hi);
     const std::string first_error = rc != X360_OK ? g_err : std::string();
     const cudaError_t e1 = cudaEventRecord(pl->ev_join, pl->s_side), e2 = cudaStreamWaitEvent(st, pl->ev_join, 0);   // always re-join
     if (rc != X360_OK) { g_err = first_error; return rc; }
@@ -1112,6 +1126,7 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
             std::vector<int> ids;
             for (int v = 0; v < params->n_views; ++v)
                 if (pl->view_group[(size_t)v] == gi) ids.push_back(v);
+            G.h_ids = ids;
             std::vector<double> Rg(ids.size() * 9);
             for (size_t i = 0; i < ids.size(); ++i) memcpy(&Rg[i * 9], params->R + 9 * ids[i], 9 * sizeof(double));
             // transposed-tile table of the group's views (TiledArgs::tr_tab), where the no-score launch can take them
@@ -1180,6 +1195,11 @@ int x360_plan_create(const x360_params *params, x360_plan **out_plan)
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_lz_k1, k1d.data(), k1d.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_lz_fix, fix.data(), fix.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && pl->path == X360_PATH_TILED && params->n_views >= x360_plan::kViewParts) {
+        bool shared_maps = false;                                           // some unit holds several views: one launch amortises their map
+        for (int gi = 0; gi < pl->n_groups; ++gi) shared_maps = shared_maps || pl->grp[gi].n_units[0] != pl->grp[gi].n_views;
+        if (!shared_maps) pl->view_parts = x360_plan::kViewParts;
+    }
     if (e != cudaSuccess) {
         x360_plan_destroy(pl);
         return fail(X360_E_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
@@ -1216,6 +1236,8 @@ int x360_plan_destroy(x360_plan *pl)
         if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
         if (pl->ev_k[i]) cudaEventDestroy(pl->ev_k[i]);
         if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
+        for (int k = 0; k < x360_plan::kViewParts; ++k)
+            if (pl->ev_part[i][k]) cudaEventDestroy(pl->ev_part[i][k]);
     }
     if (pl->jpeg) x360_jpeg_destroy(pl->jpeg);
     for (int i = 0; i < 2; ++i) {
@@ -1356,6 +1378,8 @@ static int pipe_setup(x360_plan *pl)
         if (!pl->ev_in[i]) CU(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
         if (!pl->ev_k[i]) CU(cudaEventCreateWithFlags(&pl->ev_k[i], cudaEventDisableTiming));
         if (!pl->ev_out[i]) CU(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
+        for (int k = 0; k < x360_plan::kViewParts; ++k)
+            if (!pl->ev_part[i][k]) CU(cudaEventCreateWithFlags(&pl->ev_part[i][k], cudaEventDisableTiming));
         if (!pl->d_frames[i]) CU(cudaMalloc(&pl->d_frames[i], fb * pl->chunk));
         if (!pl->d_views[i]) CU(cudaMalloc(&pl->d_views[i], vb * pl->chunk));
         if (pl->sharpen && !pl->d_sharp[i]) CU(cudaMalloc(&pl->d_sharp[i], vb * pl->chunk));
@@ -1393,6 +1417,21 @@ static int pipe_chunk(x360_plan *pl, int c, const uint8_t *frames, int f0, int n
     if (c >= 2) CU(cudaStreamWaitEvent(pl->s_k, pl->ev_out[b], 0));
     long long *ds = scores ? pl->d_sums[b] : nullptr;
     long long *ds2 = scores ? pl->d_sums[b] + (size_t)pl->chunk * V : nullptr;
+    if (n == 1 && pl->view_parts > 1 && !scores && !pl->sharpen && pl->path == X360_PATH_TILED) {
+        // a single frame of views that share no map: consecutive view ranges, each downloaded while the next is computed
+        const size_t view_bytes = (size_t)pl->g.oh * pl->g.ow * 3;
+        for (int k = 0; k < pl->view_parts; ++k) {
+            const int v_lo = (int)((long long)V * k / pl->view_parts), v_hi = (int)((long long)V * (k + 1) / pl->view_parts);
+            if (int rc = launch_tiled(pl, pl->d_frames[b], 1, pl->d_views[b], nullptr, nullptr, pl->s_k, v_lo, v_hi)) return rc;
+            CU(cudaEventRecord(pl->ev_part[b][k], pl->s_k));
+            CU(cudaStreamWaitEvent(pl->s_out, pl->ev_part[b][k], 0));
+            CU(cudaMemcpyAsync(out_views + (size_t)f0 * vb + (size_t)v_lo * view_bytes, pl->d_views[b] + (size_t)v_lo * view_bytes,
+                               (size_t)(v_hi - v_lo) * view_bytes, cudaMemcpyDeviceToHost, pl->s_out));
+        }
+        CU(cudaEventRecord(pl->ev_k[b], pl->s_k));
+        CU(cudaEventRecord(pl->ev_out[b], pl->s_out));
+        return X360_OK;
+    }
     if (int rc = x360_extract_device(pl, pl->d_frames[b], n, pl->d_views[b], (int64_t *)ds, (int64_t *)ds2, pl->s_k)) return rc;
     const uint8_t *d_result = pl->d_views[b];
     if (pl->sharpen) {                          // processor.py:379-381 on the chunk's views, still on the device

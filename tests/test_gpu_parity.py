@@ -551,6 +551,24 @@ def test_host_path_uploads_only_the_rows_the_views_read(x360, oracle, mode):
         assert ex.upload_rows() == (0, H)                               # the pole faces read every row
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["linear", "lanczos"])
+def test_single_frame_jobs_are_pipelined_by_view_range(x360, oracle, mode):
+    """Plans whose views share no map (fibonacci) extract a single-frame chunk in four launches over consecutive view ranges and
+    download each range while the next is computed (x360_extract_host): same bytes, whatever the chunking."""
+    H, W, d, fov = 768, 1536, 224, 100
+    interp = 1 if mode == "lanczos" else 0
+    for n_views in (9, 4, 3):                                        # 3 views: fewer than the four ranges, one launch
+        R = rotations(x360, x360.GeometryProcessor.generate_views(n_views, pitch_offset=-20, layout_mode="fibonacci"))
+        frames = np.stack([noise_frame(1900 + i, H, W) for i in range(3)])
+        want, _, _ = oracle.extract(frames, R, d, fov, interp, want_scores=False)
+        with x360.Extractor(H, W, d, fov, R, mode, max_batch=1) as ex:             # chunks of one frame
+            assert_same(ex.extract(frames, want_scores=False)[0], want, f"{mode} {n_views} views, three one-frame chunks", LANCZOS_TOL_LSB if interp else 0)
+            assert_same(ex.extract(frames[1:2], want_scores=False)[0], want[1:2], f"{mode} {n_views} views, one frame", LANCZOS_TOL_LSB if interp else 0)
+        with x360.Extractor(H, W, d, fov, R, mode, max_batch=4) as ex:             # a 3-frame chunk: one launch for all views
+            assert_same(ex.extract(frames, want_scores=False)[0], want, f"{mode} {n_views} views, one chunk", LANCZOS_TOL_LSB if interp else 0)
+
+
 def cv2_decode_equal(jpeg_bytes, view):
     """The file decodes (cv2) to what cv2's own encode of the view decodes to."""
     import cv2
