@@ -11,7 +11,7 @@ The directory name starts with a digit, so import it with
 from ._capi import (FLAG_FULL_UPLOAD, FLAG_FUSED_SCORE, FLAG_NO_WIDE, FLAG_PLANES, FLAG_SPLIT_SCORE, FLAG_TILE_H16, FLAG_TILE_H32, INTERP_LANCZOS4,
                     INTERP_LINEAR, X360Error, launch_count, version)
 from .analyzer import BlurAnalyzer
-from .blur_filter import BlurFilter
+from .blur_filter import BlurFilter, blur_replay
 from .extractor import Extractor, PinnedBuffer, column_only_map_x, plan_preview, remap, scores_from_sums
 from .geometry import GeometryProcessor, focal_length, rotation_stack
 from .handoff import eligible_indices, masker_input, masker_slots, normalize_mask_faces, scatter_results
@@ -24,7 +24,7 @@ from .sharpen import unsharp_mask, unsharp_mask_device
 __version__ = "0.1.0"
 
 __all__ = [
-    "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "BlurAnalyzer",
+    "GeometryProcessor", "ImageUtils", "Extractor", "ExtractionSession", "ViewResult", "BlurFilter", "blur_replay", "BlurAnalyzer",
     "PinnedBuffer", "column_only_map_x", "plan_preview", "remap", "unsharp_mask", "unsharp_mask_device", "scores_from_sums", "rotation_stack", "focal_length",
     "JpegEncoder", "encode_jpeg", "jpeg_header",
     "gather_sums", "gather_sums_by_view", "shard_axis", "shard_bounds", "shard_sizes",

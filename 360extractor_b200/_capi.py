@@ -82,6 +82,7 @@ SYMBOLS = {
     "x360_jpeg_header": (ctypes.c_int, [_i32, _i32, _i32, _vp, _i32]),
     "x360_extract_host_jpeg": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "x360_blur_state_init": (None, [ctypes.POINTER(BlurState), _i32, _i32, _dbl]),
+    "x360_blur_replay": (ctypes.c_int, [ctypes.POINTER(BlurState), _vp, _i64, _vp]),
     "x360_blur_accept": (ctypes.c_int, [ctypes.POINTER(BlurState), _dbl]),
     "x360_extract_host_filtered": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(BlurState), _vp, _i64, _vp, _vp, ctypes.POINTER(_i64)]),
     "x360_host_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp)]),

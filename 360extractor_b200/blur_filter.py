@@ -64,4 +64,22 @@ class BlurFilter:
         return [[self.accept(float(s)) for s in row] for row in scores]
 
 
-__all__ = ["BlurFilter"]
+def blur_replay(scores, enabled=True, smart=True, threshold=100.0, state=None):
+    """The accept / reject machine over a whole ``[F][V]`` score table in (frame, view) order, by the library's C restatement
+    (``x360_blur_replay``; the same decisions as ``BlurFilter.replay``, tests/test_host_api.py) -> bool ``[F][V]``.
+    ``state``: a ``_capi.BlurState`` to carry on from (and update) instead of a fresh machine."""
+    import ctypes
+
+    import numpy as np
+
+    from ._capi import BlurState, check, lib
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    if state is None:
+        state = BlurState()
+        lib().x360_blur_state_init(state, int(enabled), int(smart), float(threshold))
+    keep = np.zeros(scores.size, np.uint8)
+    check(lib().x360_blur_replay(ctypes.byref(state), scores.ctypes.data, int(scores.size), keep.ctypes.data))
+    return keep.reshape(scores.shape).astype(bool)
+
+
+__all__ = ["BlurFilter", "blur_replay"]

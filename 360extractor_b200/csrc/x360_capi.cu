@@ -2046,6 +2046,14 @@ int x360_blur_accept(x360_blur_state *st, double score)
     return blurry ? 0 : 1;
 }
 
+int x360_blur_replay(x360_blur_state *st, const double *scores, int64_t n, uint8_t *keep)
+{
+    if (!st || !keep || (n > 0 && !scores && st->enabled)) return fail(X360_E_INVALID, "null argument");
+    if (n < 0) return fail(X360_E_INVALID, "negative count");
+    for (int64_t i = 0; i < n; ++i) keep[i] = (uint8_t)x360_blur_accept(st, st->enabled ? scores[i] : 0.0);
+    return X360_OK;
+}
+
 int x360_extract_host_filtered(x360_plan *pl, const uint8_t *frames, int32_t n_frames, x360_blur_state *state, uint8_t *out_views,
                                int64_t capacity_views, uint8_t *keep, double *scores, int64_t *n_kept)
 {

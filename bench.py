@@ -491,7 +491,7 @@ def bench_sharded_cfg4(pkg, torch, dist, args, dev, local_rank, rank, world):
         ex.extract_device(d_frames, d_out, d_s, d_s2, stream=stream)
         gs, gs2 = pkg.gather_sums(d_s, d_s2, CLIP_FRAMES)                                  # NCCL all-gather (+ D2H of 2 x 12 KB)
         scores = pkg.scores_from_sums(gs, gs2, d * d)
-        keep = pkg.BlurFilter(True, True, 100.0).replay(scores)                            # sequential machine, every rank
+        keep = pkg.blur_replay(scores, smart=True, threshold=100.0)                        # sequential machine (C), every rank
 
     for _ in range(2):
         step()
@@ -506,6 +506,11 @@ def bench_sharded_cfg4(pkg, torch, dist, args, dev, local_rank, rank, world):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     kept = int(np.sum(keep))
+    # (outside the timed region) the C replay made the decisions of the Python restatement of processor.py:345-367
+    gs, gs2 = pkg.gather_sums(d_s, d_s2, CLIP_FRAMES)
+    ref_keep = np.array(pkg.BlurFilter(True, True, 100.0).replay(pkg.scores_from_sums(gs, gs2, d * d)), dtype=bool)
+    if not np.array_equal(ref_keep, np.asarray(keep, dtype=bool).reshape(ref_keep.shape)):
+        raise RuntimeError("blur_replay (C) and BlurFilter.replay (Python) disagree on the sharded clip")
     ex.close()
     del d_frames, d_out
     torch.cuda.empty_cache()

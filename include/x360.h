@@ -269,6 +269,8 @@ typedef struct x360_blur_state {
 } x360_blur_state;
 void x360_blur_state_init(x360_blur_state *state, int32_t enabled, int32_t smart, double threshold);
 int x360_blur_accept(x360_blur_state *state, double score);
+/* x360_blur_accept over a table of n scores in iteration order ((frame, view) row-major): keep[i] = 1 where the view is kept */
+int x360_blur_replay(x360_blur_state *state, const double *scores, int64_t n, uint8_t *keep);
 /*
  * x360_extract_host that downloads only the views the blur machine keeps: per chunk the Laplacian sums come back first
  * (a few bytes), the machine is replayed on the host in (frame, view) order, and one copy per KEPT view is queued — rejected

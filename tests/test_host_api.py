@@ -407,3 +407,13 @@ def test_c_blur_machine_equals_the_python_replay(x360):
             f = x360.BlurFilter(True, bool(smart), th)
             want = [f.accept(float(s)) for s in scores]
             assert run_c(scores, 1, smart, th) == (want, f.skipped, f.forced)
+            # the table form the sharded bench uses (x360_blur_replay): the same flags, and a state that carries on
+            table = scores[: len(scores) // 3 * 3].reshape(-1, 3)
+            f2 = x360.BlurFilter(True, bool(smart), th)
+            assert np.array_equal(x360.blur_replay(table, smart=bool(smart), threshold=th), np.array(f2.replay(table), dtype=bool).reshape(table.shape))
+    st = cap.BlurState()
+    L.x360_blur_state_init(st, 1, 1, 100.0)
+    f3 = x360.BlurFilter(True, True, 100.0)
+    for part in np.array_split(rng.uniform(0, 400, 90), 4):
+        assert np.array_equal(x360.blur_replay(part, state=st), np.array([f3.accept(float(s)) for s in part]))
+    assert (int(st.skipped), int(st.forced)) == (f3.skipped, f3.forced)
