@@ -554,7 +554,7 @@ def test_host_path_uploads_only_the_rows_the_views_read(x360, oracle, mode):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["linear", "lanczos"])
 def test_single_frame_jobs_are_pipelined_by_view_range(x360, oracle, mode):
-    """Plans whose views share no map (fibonacci) extract a single-frame chunk in four launches over consecutive view ranges and
+    """Plans whose views share no map (fibonacci) extract a single-frame chunk in up to eight launches over consecutive view ranges and
     download each range while the next is computed (x360_extract_host): same bytes, whatever the chunking."""
     H, W, d, fov = 768, 1536, 224, 100
     interp = 1 if mode == "lanczos" else 0
